@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""Benchmark of the plane-sweep cost-volume hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload cfg1|cfg2|...]
+
+A *step* is one pass of the hot path over one batch of synthetic frame tuples:
+one ``CostVolumeManager.forward`` (dot) / ``FeatureVolumeManager.forward`` (hero)
+call.  Default workload = BASELINE.json ``configs[1]`` (dot-product model, 1 ref +
+7 source views, 640x480 frames -> 120x160 matching maps, D=64, batch 4 per GPU),
+the configuration the metric is quoted on.  With N GPUs every rank processes its
+own batch (frames are independent: weak scaling, no data-path collective); NCCL is
+used for the barrier and the MAX-reduce of the elapsed time only.
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  roofline      algorithmic HBM bytes per sweep launch / measured launch time, against
+                MEASURED_PEAKS.json (hbm_gbs); `traffic` = ncu dram bytes per launch
+                (profiles/), null when no capture is committed
+  cpu_baseline  the oracle's reference-structured port (oracle/costvolume_oracle.py,
+                sampler="aten": the reference's op sequence) timed on the host cores
+  e2e           same metric through the public manager API with HOST (pinned) inputs
+                and outputs: H2D + sweep + D2H inside the timed region
+`--impl reference` times the CPU port alone (the reference is pure Python/PyTorch and
+/root/reference does not travel to the GPU box; the port is op-for-op the reference's
+own sequence and is pinned bit-exact against it in tests/test_oracle_vs_reference.py).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+METRIC = "cost_volume_frames_per_sec@640x480_D64_K7src"
+UNIT = "frames/s"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def algorithmic_bytes_per_frame(w, hero: bool, with_mask: bool) -> int:
+    """compulsory HBM traffic of one reference frame."""
+    HW = w.height * w.width
+    b = 4 * (w.channels * HW + w.views * w.channels * HW + w.planes * HW + HW)
+    b += 4 * (48 * w.views + 16) + 4 * w.planes
+    if hero and with_mask:
+        b += HW
+    return b
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.is_file():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic(tag: str):
+    """dram bytes per launch of the dominant kernel from a committed ncu summary."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    if p.is_file():
+        try:
+            return json.loads(p.read_text()).get(tag)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons through NVML while `active` is set."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.active = threading.Event()
+        self._stop = threading.Event()
+        self._ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self._ok = True
+        except Exception:
+            self._ok = False
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        if not self._ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            if not self.active.is_set():
+                time.sleep(0.0005)
+                continue
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+
+    def summary(self):
+        self._stop.set()
+        if not self._ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                    "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# --------------------------------------------------------------------------- #
+# CPU port (reference arm / cpu_baseline)                                     #
+# --------------------------------------------------------------------------- #
+def cpu_port_step(w, tup, weights):
+    from oracle import costvolume_oracle as O
+    if w.kind == "dot":
+        return O.forward_dot(**tup, num_depth_bins=w.planes, sampler="aten")
+    return O.forward_mlp(**tup, weights=weights, num_depth_bins=w.planes, return_mask=True,
+                         sampler="aten")
+
+
+def time_cpu_port(w, frames: int, min_seconds: float, max_reps: int):
+    """Returns (frames_per_s, cores, sample description)."""
+    from oracle import costvolume_oracle as O
+    from simplerecon_b200.synthetic import make_workload_tuple, mlp_state
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    tup = make_workload_tuple(w, batch=frames)
+    weights = O.mlp_weights_from_state_dict(mlp_state(w.views, w.channels)) if w.kind == "mlp" else None
+    with torch.inference_mode():
+        cpu_port_step(w, tup, weights)                       # warm-up
+        best, reps, t_all = float("inf"), 0, time.perf_counter()
+        while reps < max_reps and (time.perf_counter() - t_all < min_seconds or reps < 1):
+            t0 = time.perf_counter()
+            cpu_port_step(w, tup, weights)
+            best = min(best, time.perf_counter() - t0)
+            reps += 1
+    return frames / best, cores, f"{frames} frame(s) of {w.name}, best of {reps} after 1 warm-up"
+
+
+def run_reference_arm(args, w):
+    """`--impl reference`: the reference's CPU implementation (port) of the same
+    workload, all host threads, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import costvolume_oracle as O
+    from simplerecon_b200.synthetic import make_workload_tuple, mlp_state
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    frames = 1 if w.kind == "mlp" else min(w.batch, 2)     # bounded sample of one batch
+    tup = make_workload_tuple(w, batch=frames)
+    weights = O.mlp_weights_from_state_dict(mlp_state(w.views, w.channels)) if w.kind == "mlp" else None
+    with torch.inference_mode():
+        for _ in range(max(1, min(args.warmup, 2))):
+            cpu_port_step(w, tup, weights)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_port_step(w, tup, weights)
+        dt = time.perf_counter() - t0
+    fps = frames * args.steps / dt
+    sample = f"{frames} frame(s) per step of {w.name} (bounded sample of the batch)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": workload_config(w, frames, 1, "n/a (CPU)"),
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(w, batch_per_gpu, world, l2_note):
+    return {
+        "workload": w.name, "matching": w.kind, "frame": f"{4 * w.width}x{4 * w.height}",
+        "feature_map": f"{w.width}x{w.height}", "planes": w.planes, "src_views": w.views,
+        "channels": w.channels, "batch_per_gpu": batch_per_gpu, "global_batch": batch_per_gpu * world,
+        "parallelism": f"frame-sharded x{world} (no data-path collective)", "l2": l2_note,
+    }
+
+
+# --------------------------------------------------------------------------- #
+# GPU arm                                                                     #
+# --------------------------------------------------------------------------- #
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg1")
+    ap.add_argument("--variant", default="auto", choices=["auto", "generic", "fast"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    from simplerecon_b200.synthetic import CONFIGS, make_workload_tuple, mlp_state
+    w = next(c for c in CONFIGS if c.name.startswith(args.workload))
+    if args.impl == "reference":
+        run_reference_arm(args, w)
+        return
+
+    import simplerecon_b200 as S
+    from simplerecon_b200 import _native, sharding
+
+    rank, world, local = sharding.init_distributed()
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (use --impl reference for the CPU arm)"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    _native.check(_native.load().srcv_check_device())
+    _native.set_variant({"auto": 0, "generic": 1, "fast": 2}[args.variant])
+
+    # weak scaling: the per-GPU batch is the single-GPU configuration's batch
+    per_gpu = {"cfg3": 4, "cfg4": 8}.get(args.workload[:4], w.batch)
+    hero = w.kind == "mlp"
+    # rotating input sets whose footprint exceeds L2, so no step finds its inputs cached
+    in_bytes = 4 * per_gpu * (w.channels * w.height * w.width * (1 + w.views))
+    n_sets = max(2, -(-int(1.25 * L2_BYTES) // in_bytes))
+    sets_host = [make_workload_tuple(w, seed_offset=1000 * rank + i, batch=per_gpu) for i in range(n_sets)]
+    sets_dev = [{k: v.to(dev) for k, v in s.items()} for s in sets_host]
+    l2_note = (f"{n_sets} rotating input sets, {n_sets * in_bytes / 2**20:.0f} MiB > 126 MiB L2; "
+               f"outputs ({4 * per_gpu * w.planes * w.height * w.width / 2**20:.0f} MiB/step) freshly allocated")
+
+    if hero:
+        mgr = S.FeatureVolumeManager(w.height, w.width, num_depth_bins=w.planes,
+                                     mlp_channels=[0, 128, 128, 1], matching_dim_size=w.channels,
+                                     num_source_views=w.views)
+        mgr.load_state_dict({**mgr.state_dict(), **mlp_state(w.views, w.channels)})
+    else:
+        mgr = S.CostVolumeManager(w.height, w.width, num_depth_bins=w.planes)
+    mgr = mgr.to(dev).eval()
+    kw = dict(return_mask=True) if hero else {}
+
+    sampler = ClockSampler(local)
+    with torch.inference_mode():
+        def step(i):
+            return mgr(**sets_dev[i % n_sets], **kw)
+
+        for i in range(args.warmup):
+            out = step(i)
+        torch.cuda.synchronize()
+
+        # ---- value: device-resident inputs ---------------------------------
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = _native.launch_count()
+        sharding.barrier()
+        torch.cuda.synchronize()
+        sampler.active.set()
+        e0.record()
+        for i in range(args.steps):
+            out = step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        sampler.active.clear()
+        sharding.barrier()
+        ms_local = e0.elapsed_time(e1)
+        launches = _native.launch_count() - launches0
+        ms_total = sharding.max_over_ranks(ms_local, dev)
+        variant = _native.last_variant()
+
+        # ---- roofline: the sweep kernel alone, events on its own stream -----
+        _native.profile_begin(args.steps)
+        sampler.active.set()
+        for i in range(args.steps):
+            out = step(i)
+        torch.cuda.synchronize()
+        sampler.active.clear()
+        prep_ms, sweep_ms, nrec = _native.profile_end()
+
+        # ---- e2e: pinned host inputs -> H2D -> sweep -> D2H ------------------
+        pin = [{k: v.pin_memory() for k, v in s.items()} for s in sets_host[:2]]
+        h2d = sum(v.numel() * v.element_size() for v in pin[0].values())
+        out_host = None
+
+        def e2e_step(i):
+            nonlocal out_host
+            hd = {k: v.to(dev, non_blocking=True) for k, v in pin[i % 2].items()}
+            res = mgr(**hd, **kw)
+            keep = [res[0], res[1]] + ([res[3]] if res[3] is not None else [])
+            if out_host is None:
+                out_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in keep]
+            for dst, src in zip(out_host, keep):
+                dst.copy_(src, non_blocking=True)
+            return keep
+
+        for i in range(3):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        d2h = sum(t.numel() * t.element_size() for t in out_host)
+        e2e_steps = max(5, min(args.steps, 50))
+        sharding.barrier()
+        torch.cuda.synchronize()
+        sampler.active.set()
+        e0.record()
+        for i in range(e2e_steps):
+            e2e_step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        sampler.active.clear()
+        sharding.barrier()
+        e2e_ms = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
+
+    clocks = sampler.summary()
+    frames_total = per_gpu * world * args.steps
+    value = frames_total / (ms_total * 1e-3)
+    e2e_value = per_gpu * world * e2e_steps / (e2e_ms * 1e-3)
+
+    peak, peak_src = load_peaks()
+    alg_bytes = algorithmic_bytes_per_frame(w, hero, True) * per_gpu
+    sweep_avg_s = sweep_ms * 1e-3 / max(nrec, 1)
+    achieved = alg_bytes / sweep_avg_s / 1e9
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": load_traffic(f"{w.kind}:{variant}"),
+        "kernel": variant, "algorithmic_bytes_per_launch": alg_bytes,
+        "sweep_us_per_launch": sweep_avg_s * 1e6, "prep_us_per_launch": prep_ms * 1e3 / max(nrec, 1),
+        "sweep_share_of_step": (sweep_ms / max(nrec, 1)) / (ms_local / args.steps),
+        "peak_source": peak_src,
+        "note": ("HBM fraction as the metric demands; the sweep is bound by on-chip gather "
+                 "bandwidth / FP32 issue (dot) or the MLP contraction (hero), see DESIGN.md"),
+    }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(w, per_gpu, world, l2_note),
+        "roofline": roofline,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                "mode": "serial: pinned H2D -> forward -> D2H on one stream"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "kernel_variant": variant,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        frames = 1 if hero else 2
+        fps, cores, sample = time_cpu_port(w, frames, min_seconds=10.0, max_reps=5)
+        line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,174 @@
+/*
+ * srcv_b200 — C ABI of the B200-native plane-sweep cost-volume library.
+ *
+ * This is the drop-in boundary for SimpleRecon's cost-volume hot path.  The
+ * reference has no native layer (it is pure PyTorch), so each entry point below
+ * names the reference *Python* interface it replaces; the Python classes in
+ * simplerecon_b200/cost_volume.py bind these symbols through ctypes and keep the
+ * reference's class / method signatures (see INTEGRATION.md for the binding a
+ * maintainer of the reference would add).
+ *
+ * Conventions
+ *   - plain C types only: device pointers, sizes, an opaque stream handle
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - all tensors are fp32, contiguous, row-major in the reference's layouts;
+ *   - outputs and the workspace are caller-allocated (the Python side hands
+ *     PyTorch caching-allocator memory); nothing is allocated, freed or retained
+ *     by the library, and no call synchronises the device: work is enqueued on
+ *     `stream` and the call returns;
+ *   - every function returns an srcv_status (0 = ok).  Argument errors are
+ *     detected on the host before anything is launched; CUDA launch errors are
+ *     returned as SRCV_ERR_CUDA with the text available from srcv_last_error().
+ */
+#ifndef SRCV_B200_H_
+#define SRCV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRCV_ABI_VERSION 1
+
+typedef enum srcv_status {
+  SRCV_OK = 0,
+  SRCV_ERR_NULL = 1,        /* a required pointer is NULL                      */
+  SRCV_ERR_SHAPE = 2,       /* a dimension is <= 0 or out of the supported set */
+  SRCV_ERR_WORKSPACE = 3,   /* workspace too small or misaligned               */
+  SRCV_ERR_UNSUPPORTED = 4, /* valid request this build cannot serve           */
+  SRCV_ERR_CUDA = 5,        /* CUDA runtime error (see srcv_last_error)        */
+  SRCV_ERR_DEVICE = 6       /* current device is not an sm_100 part            */
+} srcv_status;
+
+/* Problem shape.  Mirrors the tensor contract of
+ * CostVolumeManager.forward (reference modules/cost_volume.py:345-380):
+ *   cur_feats (B,C,H,W)  src_feats (B,K,C,H,W)  cost (B,D,H,W).          */
+typedef struct srcv_shape {
+  int32_t B; /* reference frames in this call (batch)                        */
+  int32_t K; /* source views per frame                                       */
+  int32_t C; /* matching-feature channels                                    */
+  int32_t H; /* matching feature-map height                                  */
+  int32_t W; /* matching feature-map width                                   */
+  int32_t D; /* depth planes                                                 */
+} srcv_shape;
+
+/* How the depth hypotheses are given. */
+typedef enum srcv_planes_mode {
+  /* planes == NULL on input: the library evaluates
+   *   d_i = exp(log(min) + log(max/min) * ramp_i)
+   * (reference modules/cost_volume.py:100-136) from the DEVICE scalars
+   * min_depth / max_depth and the DEVICE ramp (D floats, the module buffer
+   * `linear_ramp_1d11`) and writes the (B,D) result to planes_out.          */
+  SRCV_PLANES_FROM_RANGE = 0,
+  /* planes is a DEVICE (B,D) array: one depth per plane and frame.         */
+  SRCV_PLANES_PER_PLANE = 1,
+  /* planes is a DEVICE (B,D,H,W) array: caller-supplied per-pixel
+   * hypotheses (the `depth_planes_bdhw` argument, modules/cost_volume.py:247) */
+  SRCV_PLANES_PER_PIXEL = 2
+} srcv_planes_mode;
+
+typedef struct srcv_planes {
+  int32_t mode;            /* srcv_planes_mode                               */
+  const float* planes;     /* (B,D) or (B,D,H,W); NULL for FROM_RANGE        */
+  const float* min_depth;  /* device scalar, FROM_RANGE only                 */
+  const float* max_depth;  /* device scalar, FROM_RANGE only                 */
+  const float* ramp;       /* device (D), FROM_RANGE only                    */
+  float* planes_out;       /* device (B,D), FROM_RANGE only (may be NULL)    */
+} srcv_planes;
+
+/* Camera block shared by both volumes (all DEVICE pointers). */
+typedef struct srcv_cameras {
+  const float* src_extrinsics; /* (B,K,4,4) src_cam_T_cur_cam               */
+  const float* src_poses;      /* (B,K,4,4) cur_cam_T_src_cam (MLP volume only; may be NULL for dot) */
+  const float* src_Ks;         /* (B,K,4,4) source intrinsics at matching scale */
+  const float* cur_invK;       /* (B,4,4) inverse intrinsics of the reference frame */
+} srcv_cameras;
+
+/* Weights of the matching MLP — the parameters of the reference's
+ * `MLP([F,H1,H2,1], disable_final_activation=True)` (modules/networks.py:129-147),
+ * in nn.Linear layout (out_features, in_features), LeakyReLU slope 0.01.    */
+typedef struct srcv_mlp_weights {
+  const float* w1; const float* b1; /* (H1,F), (H1)  F = C*(K+1)+10*K+4       */
+  const float* w2; const float* b2; /* (H2,H1), (H2)                          */
+  const float* w3; const float* b3; /* (1,H2), (1)                            */
+  int32_t hidden1;                  /* H1                                     */
+  int32_t hidden2;                  /* H2                                     */
+} srcv_mlp_weights;
+
+/* ---- library / device ------------------------------------------------- */
+int32_t srcv_abi_version(void);
+/* 0 if the CURRENT CUDA device can run this library (compute capability 10.x),
+ * else SRCV_ERR_DEVICE / SRCV_ERR_CUDA.                                      */
+int32_t srcv_check_device(void);
+const char* srcv_status_string(int32_t status);
+/* Thread-local text of the last SRCV_ERR_* raised on this thread.           */
+const char* srcv_last_error(void);
+
+/* ---- dot-product volume ----------------------------------------------- *
+ * Replaces CostVolumeManager.build_cost_volume + the argmax in
+ * CostVolumeManager.forward (reference modules/cost_volume.py:237-335,
+ * :345-380): per plane, homography-warp every source feature map into the
+ * reference frustum (bilinear, zeros padding, align_corners=False), dot it with
+ * the reference features, mask by depth validity, sum over views.
+ *   cost   (B,D,H,W) out
+ *   lowest (B,H,W)   out, plane depth at argmax_d cost (first index on ties);
+ *                    NULL to skip.                                           */
+size_t srcv_dot_workspace_bytes(const srcv_shape* shape);
+int32_t srcv_dot_forward_f32(const srcv_shape* shape,
+                             const float* cur_feats, const float* src_feats,
+                             const srcv_cameras* cams, const srcv_planes* planes,
+                             float* cost, float* lowest,
+                             void* workspace, size_t workspace_bytes,
+                             void* stream);
+
+/* ---- metadata-MLP volume ---------------------------------------------- *
+ * Replaces FeatureVolumeManager.build_cost_volume /
+ * FastFeatureVolumeManager.build_cost_volume + the argmax in forward
+ * (reference modules/cost_volume.py:451-736, :967-1164): builds the per
+ * (plane,pixel) metadata vector (warped features, reference features, validity,
+ * source depths, plane depth, per-view dot, ray angle, rays, pose measures —
+ * order of :698-723) and runs the matching MLP on it, without materialising it.
+ *   overall_mask (B,H,W) uint8 out (1 = some source view sees the pixel at the
+ *   LAST plane, :625-637); NULL when return_mask is False.                   */
+size_t srcv_mlp_workspace_bytes(const srcv_shape* shape, const srcv_mlp_weights* w);
+int32_t srcv_mlp_forward_f32(const srcv_shape* shape,
+                             const float* cur_feats, const float* src_feats,
+                             const srcv_cameras* cams, const srcv_planes* planes,
+                             const srcv_mlp_weights* weights,
+                             float* cost, float* lowest, uint8_t* overall_mask,
+                             void* workspace, size_t workspace_bytes,
+                             void* stream);
+
+/* ---- tuning / introspection ------------------------------------------- *
+ * Selects the kernel variant used by the two forward calls on this thread's
+ * next invocations (process-global).  0 = automatic choice.  Used by the tests
+ * to exercise every variant against the oracle and by bench.py to report which
+ * one ran.  Unknown values are rejected with SRCV_ERR_UNSUPPORTED.           */
+typedef enum srcv_variant {
+  SRCV_VARIANT_AUTO = 0,
+  SRCV_VARIANT_GENERIC = 1, /* shape-generic SIMT kernels                     */
+  SRCV_VARIANT_FAST = 2     /* channel-last gather / tensor-core kernels      */
+} srcv_variant;
+int32_t srcv_set_variant(int32_t variant);
+/* Name of the kernel variant the last forward call on this process launched. */
+const char* srcv_last_variant(void);
+/* Number of kernel launches issued by the library since load (monotonic).    */
+uint64_t srcv_launch_count(void);
+
+
+/* ---- per-kernel timing (benchmark support) ---------------------------- *
+ * Between srcv_profile_begin and srcv_profile_end every forward call records
+ * CUDA events on ITS stream around the prep pass and around the sweep kernel(s)
+ * (at most max_records calls are recorded; later ones run unrecorded).
+ * srcv_profile_end waits for the recorded events, returns the summed device
+ * times in milliseconds and the number of recorded calls, and releases the
+ * events.  Outside a begin/end pair nothing is recorded.                     */
+int32_t srcv_profile_begin(int32_t max_records);
+int32_t srcv_profile_end(double* prep_ms_total, double* sweep_ms_total, int32_t* n_records);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRCV_B200_H_ */

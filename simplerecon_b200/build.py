@@ -1,0 +1,63 @@
+"""Builds ``lib/libsrcv_b200.so`` in-tree with nvcc for sm_100a.
+
+    python -m simplerecon_b200.build [--force] [--verbose]
+
+Plain ``nvcc -shared`` (no torch headers: the library is a C ABI, torch only
+supplies device memory and streams at run time).  The .so is git-ignored but
+travels with the working tree to the GPU box.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+SRC = sorted((PKG / "csrc").glob("*.cu"))
+HDR = sorted((PKG / "csrc").glob("*.cuh")) + sorted((PKG / "csrc").glob("*.h")) + \
+    [PKG.parent / "include" / "srcv_b200.h"]
+OUT = PKG / "lib" / "libsrcv_b200.so"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def nvcc_path() -> str:
+    for c in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and Path(c).is_file():
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def up_to_date() -> bool:
+    if not OUT.is_file():
+        return False
+    t = OUT.stat().st_mtime
+    return all(p.stat().st_mtime <= t for p in SRC + HDR)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and up_to_date():
+        return OUT
+    OUT.parent.mkdir(parents=True, exist_ok=True)
+    cmd = [nvcc_path(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []),
+           "-o", str(OUT), *map(str, SRC)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed ({r.returncode}): {' '.join(cmd)}")
+    return OUT
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    a = ap.parse_args()
+    print(build(a.force, a.verbose))

@@ -1,0 +1,288 @@
+"""Drop-in cost-volume managers backed by the sm_100a kernels.
+
+Class names, constructor signatures, method names, ``forward`` signature / return
+tuple, buffers and ``state_dict`` keys follow the reference's
+``modules/cost_volume.py`` (``CostVolumeManager`` :13-380, ``FeatureVolumeManager``
+:383-746, ``FastFeatureVolumeManager`` :749-1164) so that
+``experiment_modules/depth_model.py:162-176, 362-372`` and the ``isinstance`` /
+``to_fast()`` swaps in ``test.py:196-198`` work unchanged.  The sweep itself is one
+call into ``libsrcv_b200.so`` (include/srcv_b200.h) on the current CUDA stream.
+
+Contract at the boundary: fp32 CUDA tensors, inference only.
+Anything else raises — there is no PyTorch / CPU fallback on this path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch import Tensor, nn
+
+from . import _native
+from .geometry import BackprojectDepth, Project3D
+from .networks import MLP
+
+
+def _ptr(t: Tensor | None):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _f32c(t: Tensor, name: str, device) -> Tensor:
+    if not torch.is_tensor(t):
+        raise TypeError(f"{name} must be a tensor")
+    if t.dtype != torch.float32:
+        raise ValueError(f"{name} must be float32 (got {t.dtype}); the fused path is fp32-only")
+    if t.device != device:
+        raise ValueError(f"{name} is on {t.device}, expected {device}")
+    return t.contiguous()
+
+
+class CostVolumeManager(nn.Module):
+    """Dot-product plane-sweep cost volume (reference modules/cost_volume.py:13-380).
+
+    ``matching_dim_size`` and ``num_source_views`` are accepted and ignored, as in
+    the reference (:27-34).
+    """
+
+    def __init__(self, matching_height, matching_width, num_depth_bins=64,
+                 matching_dim_size=None, num_source_views=None):
+        super().__init__()
+        self.num_depth_bins = num_depth_bins
+        self.matching_height = matching_height
+        self.matching_width = matching_width
+        self.initialise_for_projection()
+
+    # -- reference :58-74 -----------------------------------------------------
+    def initialise_for_projection(self):
+        ramp = torch.linspace(0, 1, self.num_depth_bins).view(1, self.num_depth_bins, 1, 1)
+        self.register_buffer("linear_ramp_1d11", ramp)
+        self.backprojector = BackprojectDepth(height=self.matching_height, width=self.matching_width)
+        self.projector = Project3D()
+
+    # -- reference :77-97 -----------------------------------------------------
+    def get_mask(self, pix_coords_bk2hw):
+        x, y = pix_coords_bk2hw[:, :, 0], pix_coords_bk2hw[:, :, 1]
+        return (x > 2) & (x < self.matching_width - 2) & (y > 2) & (y < self.matching_height - 2)
+
+    # -- reference :100-136 ---------------------------------------------------
+    def generate_depth_planes(self, batch_size: int, min_depth: Tensor, max_depth: Tensor) -> Tensor:
+        ramp = self.linear_ramp_1d11.expand(batch_size, self.num_depth_bins, 1, 1)
+        planes = torch.exp(torch.log(min_depth) + torch.log(max_depth / min_depth) * ramp)
+        return planes.expand(batch_size, self.num_depth_bins, self.matching_height, self.matching_width)
+
+    def warp_features(self, *args, **kwargs):
+        raise NotImplementedError(
+            "warp_features materialises the (B,K,C,H,W) warped tensor per plane; the fused "
+            "kernels never form it.  Use build_cost_volume / forward.")
+
+    # -- reference :338-342 ---------------------------------------------------
+    def indices_to_disparity(self, indices, depth_planes_bdhw):
+        return torch.gather(depth_planes_bdhw, dim=1, index=indices.unsqueeze(1)).squeeze(1)
+
+    # ------------------------------------------------------------------------
+    # shared argument handling
+    # ------------------------------------------------------------------------
+    def _prepare(self, cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK,
+                 min_depth, max_depth, depth_planes_bdhw, need_poses):
+        if not torch.is_tensor(src_feats) or src_feats.dim() != 5:
+            raise ValueError("src_feats must be a (B,K,C,H,W) tensor")
+        dev = src_feats.device
+        if dev.type != "cuda":
+            raise RuntimeError(
+                "simplerecon_b200 cost volumes run on CUDA (sm_100a) only; got tensors on "
+                f"{dev}.  There is no CPU fallback.")
+        if torch.is_grad_enabled() and (
+                cur_feats.requires_grad or src_feats.requires_grad
+                or any(p.requires_grad for p in self.parameters())
+        ):
+            raise NotImplementedError(
+                "the fused cost volume is forward-only; call it under torch.no_grad() / "
+                "torch.inference_mode() (the fused backward is the next scope row, SURVEY.md §8f-1)")
+        B, K, Cc, H, W = src_feats.shape
+        if (H, W) != (self.matching_height, self.matching_width):
+            raise ValueError(f"feature map {H}x{W} does not match the manager's "
+                             f"{self.matching_height}x{self.matching_width}")
+        if tuple(cur_feats.shape) != (B, Cc, H, W):
+            raise ValueError(f"cur_feats shape {tuple(cur_feats.shape)} != {(B, Cc, H, W)}")
+        for name, t, shp in (("src_extrinsics", src_extrinsics, (B, K, 4, 4)),
+                             ("src_Ks", src_Ks, (B, K, 4, 4)),
+                             ("cur_invK", cur_invK, (B, 4, 4))):
+            if tuple(t.shape) != shp:
+                raise ValueError(f"{name} shape {tuple(t.shape)} != {shp}")
+        if need_poses and tuple(src_poses.shape) != (B, K, 4, 4):
+            raise ValueError(f"src_poses shape {tuple(src_poses.shape)} != {(B, K, 4, 4)}")
+        t = dict(
+            cur=_f32c(cur_feats, "cur_feats", dev), src=_f32c(src_feats, "src_feats", dev),
+            E=_f32c(src_extrinsics, "src_extrinsics", dev), Ks=_f32c(src_Ks, "src_Ks", dev),
+            invK=_f32c(cur_invK, "cur_invK", dev),
+            poses=_f32c(src_poses, "src_poses", dev) if need_poses else None,
+        )
+        D = self.num_depth_bins
+        pl = _native.Planes()
+        keep = []
+        if depth_planes_bdhw is None:
+            mn = _f32c(min_depth.to(dev), "min_depth", dev).reshape(-1)
+            mx = _f32c(max_depth.to(dev), "max_depth", dev).reshape(-1)
+            if mn.numel() != 1 or mx.numel() != 1:
+                raise ValueError("min_depth / max_depth must hold one value (shape (1,1,1,1))")
+            ramp = _f32c(self.linear_ramp_1d11, "linear_ramp_1d11", dev).reshape(-1)
+            planes_bd = torch.empty(B, D, device=dev, dtype=torch.float32)
+            pl.mode = _native.PLANES_FROM_RANGE
+            pl.planes, pl.min_depth, pl.max_depth = None, mn.data_ptr(), mx.data_ptr()
+            pl.ramp, pl.planes_out = ramp.data_ptr(), planes_bd.data_ptr()
+            keep += [mn, mx, ramp]
+            planes_ret = planes_bd.view(B, D, 1, 1).expand(B, D, H, W)   # expanded view, like :129-134
+        else:
+            if depth_planes_bdhw.dim() != 4 or tuple(depth_planes_bdhw.shape[::2]) != (B, H) \
+                    or depth_planes_bdhw.shape[3] != W:
+                raise ValueError("depth_planes_bdhw must be (B,D,H,W)")
+            # the per-plane managers sweep the first `num_depth_bins` planes (:305, :557);
+            # the fast one takes the tensor's own plane count (:1065)
+            D = depth_planes_bdhw.shape[1] if isinstance(self, FastFeatureVolumeManager) \
+                else self.num_depth_bins
+            if depth_planes_bdhw.shape[1] < D:
+                raise ValueError(f"depth_planes_bdhw holds {depth_planes_bdhw.shape[1]} planes, "
+                                 f"the manager sweeps {D}")
+            if depth_planes_bdhw.dtype != torch.float32 or depth_planes_bdhw.device != dev:
+                raise ValueError("depth_planes_bdhw must be float32 on the features' device")
+            st = depth_planes_bdhw.stride()
+            if (st[2] == 0 or H == 1) and (st[3] == 0 or W == 1):
+                per = depth_planes_bdhw[:, :D, 0, 0].contiguous()
+                pl.mode = _native.PLANES_PER_PLANE
+            else:
+                per = depth_planes_bdhw[:, :D].contiguous()
+                pl.mode = _native.PLANES_PER_PIXEL
+            pl.planes = per.data_ptr()
+            pl.min_depth = pl.max_depth = pl.ramp = pl.planes_out = None
+            keep.append(per)
+            planes_ret = depth_planes_bdhw
+        shape = _native.Shape(B, K, Cc, H, W, D)
+        cams = _native.Cameras(t["E"].data_ptr(), t["poses"].data_ptr() if need_poses else None,
+                               t["Ks"].data_ptr(), t["invK"].data_ptr())
+        return dev, shape, t, cams, pl, planes_ret, keep
+
+    # -- reference :237-335 ---------------------------------------------------
+    def build_cost_volume(self, cur_feats: Tensor, src_feats: Tensor, src_extrinsics: Tensor,
+                          src_poses: Tensor, src_Ks: Tensor, cur_invK: Tensor, min_depth: Tensor,
+                          max_depth: Tensor, depth_planes_bdhw: Tensor = None,
+                          return_mask: bool = False):
+        cost, _, planes, mask = self._run(cur_feats, src_feats, src_extrinsics, src_poses, src_Ks,
+                                          cur_invK, min_depth, max_depth, depth_planes_bdhw,
+                                          return_mask, want_lowest=False)
+        return cost, planes, mask
+
+    def _run(self, cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK, min_depth,
+             max_depth, depth_planes_bdhw, return_mask, want_lowest):
+        # `src_poses` and `return_mask` are ignored by the dot-product volume (:286)
+        lib = _native.load()
+        dev, shape, t, cams, pl, planes_ret, keep = self._prepare(
+            cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK, min_depth,
+            max_depth, depth_planes_bdhw, need_poses=False)
+        with torch.cuda.device(dev):
+            cost = torch.empty(shape.B, shape.D, shape.H, shape.W, device=dev, dtype=torch.float32)
+            lowest = torch.empty(shape.B, shape.H, shape.W, device=dev, dtype=torch.float32) \
+                if want_lowest else None
+            nbytes = lib.srcv_dot_workspace_bytes(C.byref(shape))
+            ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _native.check(lib.srcv_dot_forward_f32(
+                C.byref(shape), _ptr(t["cur"]), _ptr(t["src"]), C.byref(cams), C.byref(pl),
+                _ptr(cost), _ptr(lowest), _ptr(ws), nbytes, C.c_void_p(stream)))
+        return cost, lowest, planes_ret, None
+
+    # -- reference :345-380 ---------------------------------------------------
+    def forward(self, cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK,
+                min_depth, max_depth, depth_planes_bdhw=None, return_mask=False):
+        """Returns ``(cost_volume, lowest_cost, depth_planes_bdhw, overall_mask_bhw)``.
+        ``lowest_cost`` is the plane depth at the ARGMAX of the volume, as in the
+        reference (:374-378)."""
+        return self._run(cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK,
+                         min_depth, max_depth, depth_planes_bdhw, return_mask, want_lowest=True)
+
+
+class FeatureVolumeManager(CostVolumeManager):
+    """Metadata-MLP plane-sweep volume (reference modules/cost_volume.py:383-746)."""
+
+    _banner = "FeatureVolumeManager"
+
+    def __init__(self, matching_height, matching_width, num_depth_bins=64,
+                 mlp_channels=[202, 128, 128, 1], matching_dim_size=16, num_source_views=7):
+        super().__init__(matching_height, matching_width, num_depth_bins)
+        # channel bookkeeping of :420-435.  The shared default list is updated in place,
+        # exactly like the reference (:429) — callers relying on that quirk keep working.
+        mlp_channels[0] = (matching_dim_size * (1 + num_source_views)   # visual
+                           + (1 + num_source_views)                      # depths
+                           + 3 * (1 + num_source_views)                  # rays
+                           + num_source_views                            # ray angles
+                           + num_source_views                            # masks
+                           + num_source_views                            # dots
+                           + 3 * num_source_views)                       # pose measures
+        self.mlp = MLP(channel_list=mlp_channels, disable_final_activation=True)
+        print(f" simplerecon_b200 {self._banner}: {num_source_views} source views, "
+              f"MLP channels {mlp_channels} (sm_100a fused sweep) ")
+
+    def _mlp_weights(self, dev, n_features):
+        lin = [m for m in self.mlp.net if isinstance(m, nn.Linear)]
+        acts = [m for m in self.mlp.net if not isinstance(m, nn.Linear)]
+        if len(lin) != 3 or len(self.mlp.net) != 5 or not all(isinstance(a, nn.LeakyReLU) for a in acts) \
+                or any(abs(a.negative_slope - 0.01) > 0 for a in acts) or lin[2].out_features != 1:
+            raise NotImplementedError(
+                "the fused kernels implement the reference's F->H1->H2->1 LeakyReLU(0.01) MLP; "
+                f"got {self.mlp.net}")
+        if lin[0].in_features != n_features:
+            raise ValueError(f"MLP expects {lin[0].in_features} input channels but K and C of the "
+                             f"inputs give {n_features}")
+        ts = []
+        for l in lin:
+            if l.bias is None:
+                raise NotImplementedError("MLP layers without bias are not supported")
+            ts += [_f32c(l.weight.detach(), "mlp weight", dev), _f32c(l.bias.detach(), "mlp bias", dev)]
+        w = _native.MlpWeights(*[x.data_ptr() for x in ts], lin[0].out_features, lin[1].out_features)
+        return w, ts
+
+    def _run(self, cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK, min_depth,
+             max_depth, depth_planes_bdhw, return_mask, want_lowest):
+        lib = _native.load()
+        dev, shape, t, cams, pl, planes_ret, keep = self._prepare(
+            cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK, min_depth,
+            max_depth, depth_planes_bdhw, need_poses=True)
+        n_features = shape.C * (shape.K + 1) + 10 * shape.K + 4
+        w, wkeep = self._mlp_weights(dev, n_features)
+        with torch.cuda.device(dev):
+            cost = torch.empty(shape.B, shape.D, shape.H, shape.W, device=dev, dtype=torch.float32)
+            lowest = torch.empty(shape.B, shape.H, shape.W, device=dev, dtype=torch.float32) \
+                if want_lowest else None
+            mask = torch.empty(shape.B, shape.H, shape.W, device=dev, dtype=torch.uint8) \
+                if return_mask else None
+            nbytes = lib.srcv_mlp_workspace_bytes(C.byref(shape), C.byref(w))
+            if nbytes == 0:
+                raise NotImplementedError(
+                    f"MLP widths ({w.hidden1},{w.hidden2}) are not supported by the fused kernels")
+            ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _native.check(lib.srcv_mlp_forward_f32(
+                C.byref(shape), _ptr(t["cur"]), _ptr(t["src"]), C.byref(cams), C.byref(pl),
+                C.byref(w), _ptr(cost), _ptr(lowest), _ptr(mask), _ptr(ws), nbytes,
+                C.c_void_p(stream)))
+        return cost, lowest, planes_ret, (mask.bool() if mask is not None else None)
+
+    # -- reference :739-746 ---------------------------------------------------
+    def to_fast(self) -> "FastFeatureVolumeManager":
+        manager = FastFeatureVolumeManager(self.matching_height, self.matching_width,
+                                           num_depth_bins=self.num_depth_bins)
+        manager.mlp = self.mlp
+        return manager
+
+
+class FastFeatureVolumeManager(FeatureVolumeManager):
+    """Same volume as ``FeatureVolumeManager``; in the reference (:749-1164) this class
+    trades 550 MB + 993 MB of materialised tensors per frame for fewer launches.  The
+    fused kernel has neither cost, so both classes run the same sweep; the subclass
+    exists because ``test.py:196-198`` swaps it in via ``to_fast()``."""
+
+    _banner = "FastFeatureVolumeManager"
+
+    def __init__(self, matching_height, matching_width, num_depth_bins=64,
+                 mlp_channels=[202, 128, 128, 1], matching_dim_size=16, num_source_views=7):
+        super().__init__(matching_height, matching_width, num_depth_bins, mlp_channels,
+                         matching_dim_size, num_source_views)

@@ -1,0 +1,256 @@
+// extern "C" surface of libsrcv_b200.so — see include/srcv_b200.h for the contract
+// and the reference interfaces each entry point stands in for.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "srcv_kernels.h"
+
+namespace srcv {
+
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_variant{SRCV_VARIANT_AUTO};
+static const char* g_last_variant = "none";
+static thread_local char g_err[512] = "";
+
+void note_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+static int32_t fail(int32_t code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static int32_t cuda_fail(cudaError_t e, const char* where) {
+  return fail(SRCV_ERR_CUDA, "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+// ---- optional per-kernel timing ------------------------------------------------
+struct ProfRecord { cudaEvent_t e[3]; };
+static std::vector<ProfRecord> g_prof;
+static int g_prof_used = 0;
+static bool g_prof_on = false;
+static std::mutex g_prof_mu;
+
+static ProfRecord* prof_next() {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof_on || g_prof_used >= (int)g_prof.size()) return nullptr;
+  return &g_prof[g_prof_used++];
+}
+
+static int32_t check_shape(const srcv_shape* s) {
+  if (!s) return fail(SRCV_ERR_NULL, "shape is NULL");
+  if (s->B <= 0 || s->K <= 0 || s->C <= 0 || s->H <= 0 || s->W <= 0 || s->D <= 0)
+    return fail(SRCV_ERR_SHAPE, "non-positive dimension B=%d K=%d C=%d H=%d W=%d D=%d", s->B, s->K,
+                s->C, s->H, s->W, s->D);
+  if ((long long)s->H * s->W > (1ll << 26) || s->K > 64 || s->C > 1024 ||
+      (long long)s->B * s->D * s->H * s->W > (1ll << 40))
+    return fail(SRCV_ERR_SHAPE, "dimension out of supported range");
+  return SRCV_OK;
+}
+
+static int32_t check_common(const srcv_shape* s, const float* cur, const float* src,
+                            const srcv_cameras* cams, const srcv_planes* pl, const float* cost,
+                            bool need_poses) {
+  if (int32_t e = check_shape(s)) return e;
+  if (!cur || !src || !cost) return fail(SRCV_ERR_NULL, "cur_feats/src_feats/cost is NULL");
+  if (!cams || !cams->src_extrinsics || !cams->src_Ks || !cams->cur_invK)
+    return fail(SRCV_ERR_NULL, "camera block incomplete");
+  if (need_poses && !cams->src_poses) return fail(SRCV_ERR_NULL, "src_poses is NULL");
+  if (!pl) return fail(SRCV_ERR_NULL, "planes descriptor is NULL");
+  switch (pl->mode) {
+    case SRCV_PLANES_FROM_RANGE:
+      if (!pl->min_depth || !pl->max_depth || !pl->ramp)
+        return fail(SRCV_ERR_NULL, "FROM_RANGE needs min_depth, max_depth and ramp");
+      break;
+    case SRCV_PLANES_PER_PLANE:
+    case SRCV_PLANES_PER_PIXEL:
+      if (!pl->planes) return fail(SRCV_ERR_NULL, "planes pointer is NULL");
+      break;
+    default:
+      return fail(SRCV_ERR_UNSUPPORTED, "unknown planes mode %d", pl->mode);
+  }
+  return SRCV_OK;
+}
+
+static int32_t check_workspace(void* ws, size_t have, size_t need) {
+  if (!ws) return fail(SRCV_ERR_NULL, "workspace is NULL (need %zu bytes)", need);
+  if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0)
+    return fail(SRCV_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+  if (have < need) return fail(SRCV_ERR_WORKSPACE, "workspace too small: %zu < %zu", have, need);
+  return SRCV_OK;
+}
+
+static bool use_fast_dot(const srcv_shape& s) {
+  const int v = g_variant.load();
+  if (v == SRCV_VARIANT_GENERIC) return false;
+  return dot_fast_supported(s);
+}
+
+}  // namespace srcv
+
+using namespace srcv;
+
+extern "C" {
+
+int32_t srcv_abi_version(void) { return SRCV_ABI_VERSION; }
+
+int32_t srcv_check_device(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
+  if (major != 10) return fail(SRCV_ERR_DEVICE, "device %d has compute capability %d.x; this library is built for sm_100a only", dev, major);
+  return SRCV_OK;
+}
+
+const char* srcv_status_string(int32_t st) {
+  switch (st) {
+    case SRCV_OK: return "ok";
+    case SRCV_ERR_NULL: return "null pointer";
+    case SRCV_ERR_SHAPE: return "bad shape";
+    case SRCV_ERR_WORKSPACE: return "bad workspace";
+    case SRCV_ERR_UNSUPPORTED: return "unsupported";
+    case SRCV_ERR_CUDA: return "cuda error";
+    case SRCV_ERR_DEVICE: return "unsupported device";
+    default: return "unknown status";
+  }
+}
+
+const char* srcv_last_error(void) { return g_err; }
+
+int32_t srcv_set_variant(int32_t v) {
+  if (v != SRCV_VARIANT_AUTO && v != SRCV_VARIANT_GENERIC && v != SRCV_VARIANT_FAST)
+    return fail(SRCV_ERR_UNSUPPORTED, "unknown variant %d", v);
+  g_variant.store(v);
+  return SRCV_OK;
+}
+
+const char* srcv_last_variant(void) { return g_last_variant; }
+
+uint64_t srcv_launch_count(void) { return g_launches.load(); }
+
+size_t srcv_dot_workspace_bytes(const srcv_shape* s) {
+  if (check_shape(s) != SRCV_OK) return 0;
+  return carve_workspace(*s, nullptr, dot_fast_supported(*s), 0).bytes;
+}
+
+int32_t srcv_dot_forward_f32(const srcv_shape* s, const float* cur, const float* src,
+                             const srcv_cameras* cams, const srcv_planes* pl, float* cost,
+                             float* lowest, void* workspace, size_t workspace_bytes, void* stream_) {
+  if (int32_t e = check_common(s, cur, src, cams, pl, cost, false)) return e;
+  const bool fast = use_fast_dot(*s);
+  if (g_variant.load() == SRCV_VARIANT_FAST && !fast)
+    return fail(SRCV_ERR_UNSUPPORTED, "fast dot variant needs C == 16 and K <= 8");
+  const Workspace need = carve_workspace(*s, nullptr, dot_fast_supported(*s), 0);
+  if (int32_t e = check_workspace(workspace, workspace_bytes, need.bytes)) return e;
+  Workspace ws = carve_workspace(*s, workspace, dot_fast_supported(*s), 0);
+  if (!fast) ws.src_nhwc = nullptr;  // skip the channel-last copy
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ProfRecord* pr = prof_next();
+  if (pr) cudaEventRecord(pr->e[0], stream);
+  cudaError_t err = launch_prep(*s, *cams, *pl, src, ws, false, stream);
+  if (err != cudaSuccess) return cuda_fail(err, "prep");
+  if (pr) cudaEventRecord(pr->e[1], stream);
+  const bool per_pixel = pl->mode == SRCV_PLANES_PER_PIXEL;
+  const float* planes = pl->mode == SRCV_PLANES_FROM_RANGE ? ws.planes : pl->planes;
+  if (fast) {
+    g_last_variant = "dot_fast_nhwc_quadlane";
+    err = launch_dot_fast(*s, cur, ws, planes, per_pixel, cost, lowest, stream);
+  } else {
+    g_last_variant = "dot_generic";
+    err = launch_dot_generic(*s, cur, src, ws, planes, per_pixel, cost, lowest, stream);
+  }
+  if (err != cudaSuccess) return cuda_fail(err, g_last_variant);
+  if (pr) cudaEventRecord(pr->e[2], stream);
+  return SRCV_OK;
+}
+
+static int32_t check_weights(const srcv_shape* s, const srcv_mlp_weights* w) {
+  if (!w) return fail(SRCV_ERR_NULL, "weights is NULL");
+  if (!w->w1 || !w->b1 || !w->w2 || !w->b2 || !w->w3 || !w->b3)
+    return fail(SRCV_ERR_NULL, "a weight pointer is NULL");
+  if (w->hidden1 <= 0 || w->hidden2 <= 0) return fail(SRCV_ERR_SHAPE, "hidden widths must be positive");
+  if (!mlp_generic_supported(*s, *w))
+    return fail(SRCV_ERR_UNSUPPORTED, "MLP widths (%d,%d) / feature count not supported by this build (hidden <= 128)", w->hidden1, w->hidden2);
+  return SRCV_OK;
+}
+
+size_t srcv_mlp_workspace_bytes(const srcv_shape* s, const srcv_mlp_weights* w) {
+  if (check_shape(s) != SRCV_OK || !w) return 0;
+  if (!mlp_generic_supported(*s, *w)) return 0;
+  return carve_workspace(*s, nullptr, false, mlp_generic_extra_bytes(*s, *w)).bytes;
+}
+
+int32_t srcv_mlp_forward_f32(const srcv_shape* s, const float* cur, const float* src,
+                             const srcv_cameras* cams, const srcv_planes* pl,
+                             const srcv_mlp_weights* w, float* cost, float* lowest,
+                             uint8_t* overall_mask, void* workspace, size_t workspace_bytes,
+                             void* stream_) {
+  if (int32_t e = check_common(s, cur, src, cams, pl, cost, true)) return e;
+  if (int32_t e = check_weights(s, w)) return e;
+  const size_t extra = mlp_generic_extra_bytes(*s, *w);
+  const Workspace need = carve_workspace(*s, nullptr, false, extra);
+  if (int32_t e = check_workspace(workspace, workspace_bytes, need.bytes)) return e;
+  Workspace ws = carve_workspace(*s, workspace, false, extra);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ProfRecord* pr = prof_next();
+  if (pr) cudaEventRecord(pr->e[0], stream);
+  cudaError_t err = launch_prep(*s, *cams, *pl, src, ws, true, stream);
+  if (err != cudaSuccess) return cuda_fail(err, "prep");
+  if (pr) cudaEventRecord(pr->e[1], stream);
+  const bool per_pixel = pl->mode == SRCV_PLANES_PER_PIXEL;
+  const float* planes = pl->mode == SRCV_PLANES_FROM_RANGE ? ws.planes : pl->planes;
+  g_last_variant = "mlp_generic_fp32";
+  err = launch_mlp_generic(*s, cur, src, ws, planes, per_pixel, *w, cost, lowest, overall_mask, stream);
+  if (err != cudaSuccess) return cuda_fail(err, g_last_variant);
+  if (pr) cudaEventRecord(pr->e[2], stream);
+  return SRCV_OK;
+}
+
+int32_t srcv_profile_begin(int32_t max_records) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (g_prof_on) return fail(SRCV_ERR_UNSUPPORTED, "profiling already active");
+  if (max_records <= 0 || max_records > 100000) return fail(SRCV_ERR_SHAPE, "max_records out of range");
+  g_prof.resize(max_records);
+  for (auto& r : g_prof)
+    for (auto& e : r.e) {
+      cudaError_t err = cudaEventCreate(&e);
+      if (err != cudaSuccess) { g_prof.clear(); return cuda_fail(err, "cudaEventCreate"); }
+    }
+  g_prof_used = 0;
+  g_prof_on = true;
+  return SRCV_OK;
+}
+
+int32_t srcv_profile_end(double* prep_ms_total, double* sweep_ms_total, int32_t* n_records) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof_on) return fail(SRCV_ERR_UNSUPPORTED, "profiling not active");
+  double prep = 0.0, sweep = 0.0;
+  int32_t st = SRCV_OK;
+  for (int i = 0; i < g_prof_used; ++i) {
+    cudaError_t err = cudaEventSynchronize(g_prof[i].e[2]);
+    float a = 0.f, b = 0.f;
+    if (err == cudaSuccess) err = cudaEventElapsedTime(&a, g_prof[i].e[0], g_prof[i].e[1]);
+    if (err == cudaSuccess) err = cudaEventElapsedTime(&b, g_prof[i].e[1], g_prof[i].e[2]);
+    if (err != cudaSuccess) { st = cuda_fail(err, "profile events"); break; }
+    prep += a; sweep += b;
+  }
+  if (prep_ms_total) *prep_ms_total = prep;
+  if (sweep_ms_total) *sweep_ms_total = sweep;
+  if (n_records) *n_records = g_prof_used;
+  for (auto& r : g_prof) for (auto& e : r.e) cudaEventDestroy(e);
+  g_prof.clear();
+  g_prof_used = 0;
+  g_prof_on = false;
+  return st;
+}
+
+}  // extern "C"

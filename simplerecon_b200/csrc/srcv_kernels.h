@@ -1,0 +1,53 @@
+// Internal host-side launch interface between srcv_api.cu and the kernel files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/srcv_b200.h"
+#include "srcv_common.cuh"
+
+namespace srcv {
+
+// Workspace carve-up (all offsets 256-byte aligned).
+struct Workspace {
+  float* planes;        // (B,D) plane depths (FROM_RANGE / PER_PLANE copy)
+  ViewParams* views;    // (B,K)
+  FrameParams* frames;  // (B)
+  float* src_nhwc;      // (B,K,H,W,C) channel-last copy of src_feats, or nullptr
+  float* extra;         // variant-specific scratch, or nullptr
+  size_t bytes;         // total bytes needed
+};
+
+Workspace carve_workspace(const srcv_shape& s, void* base, bool want_nhwc, size_t extra_bytes);
+
+// counts kernel launches for srcv_launch_count()
+void note_launch(int n = 1);
+
+// prep: view/frame params, plane depths, optional NCHW->NHWC copy of src_feats.
+cudaError_t launch_prep(const srcv_shape& s, const srcv_cameras& cams, const srcv_planes& pl,
+                        const float* src_feats, const Workspace& ws, bool need_poses,
+                        cudaStream_t stream);
+
+// dot-product volume
+cudaError_t launch_dot_generic(const srcv_shape& s, const float* cur, const float* src,
+                               const Workspace& ws, const float* planes, bool per_pixel,
+                               float* cost, float* lowest, cudaStream_t stream);
+bool dot_fast_supported(const srcv_shape& s);
+cudaError_t launch_dot_fast(const srcv_shape& s, const float* cur, const Workspace& ws,
+                            const float* planes, bool per_pixel, float* cost, float* lowest,
+                            cudaStream_t stream);
+
+// metadata-MLP volume
+bool mlp_generic_supported(const srcv_shape& s, const srcv_mlp_weights& w);
+size_t mlp_generic_extra_bytes(const srcv_shape& s, const srcv_mlp_weights& w);
+cudaError_t launch_mlp_generic(const srcv_shape& s, const float* cur, const float* src,
+                               const Workspace& ws, const float* planes, bool per_pixel,
+                               const srcv_mlp_weights& w, float* cost, float* lowest,
+                               uint8_t* mask, cudaStream_t stream);
+
+// argmax over planes -> plane depth (used by variants that do not fuse it)
+cudaError_t launch_argmax(const srcv_shape& s, const float* cost, const float* planes,
+                          bool per_pixel, float* lowest, cudaStream_t stream);
+
+}  // namespace srcv

@@ -1,0 +1,190 @@
+// Prep pass: everything that is constant over the sweep, in ONE launch.
+//
+//  * per (frame, view): the plane-induced homography pieces Hm, t (see
+//    srcv_common.cuh), the source camera centre, and the DVMVS pose measures
+//    (reference utils/geometry_utils.py:178-191);
+//  * per frame: invK[:3,:3] for the rays (utils/geometry_utils.py:56);
+//  * plane depths  d_i = exp(log(min) + log(max/min) ramp_i)
+//    (reference modules/cost_volume.py:124-127) when the caller gives a range;
+//  * optionally the channel-last (B,K,H,W,C) copy of the source features that the
+//    fast kernels gather from: one 64-byte texel per (view, pixel) so a bilinear
+//    tap is four 16-byte vector loads instead of C scalar ones.
+#include "srcv_kernels.h"
+
+namespace srcv {
+
+namespace {
+
+__device__ void view_params(const float* __restrict__ Kmat, const float* __restrict__ E,
+                            const float* __restrict__ invK, const float* __restrict__ pose,
+                            ViewParams* out) {
+  // P = K @ E (rows 0..2), fp64 then one rounding.
+  double P[3][4];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double a = 0.0;
+#pragma unroll
+      for (int l = 0; l < 4; ++l) a += (double)Kmat[i * 4 + l] * (double)E[l * 4 + j];
+      P[i][j] = a;
+    }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      double a = 0.0;
+#pragma unroll
+      for (int l = 0; l < 3; ++l) a += P[i][l] * (double)invK[l * 4 + j];
+      out->Hm[i * 3 + j] = (float)a;
+    }
+    out->t[i] = (float)P[i][3];
+  }
+  if (pose != nullptr) {
+    const float t0 = pose[3], t1 = pose[7], t2 = pose[11];
+    out->centre[0] = t0; out->centre[1] = t1; out->centre[2] = t2;
+    // pose_distance, fp32 like the reference
+    const float tr = __fadd_rn(__fadd_rn(pose[0], pose[5]), pose[10]);
+    const float rm = sqrtf(__fmul_rn(2.0f, __fadd_rn(1.0f, -__fdiv_rn(fminf(3.0f, tr), 3.0f))));
+    const float tm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(t0, t0), __fmul_rn(t1, t1)), __fmul_rn(t2, t2)));
+    out->rmeas = rm;
+    out->tmeas = tm;
+    out->comb = sqrtf(__fadd_rn(__fmul_rn(tm, tm), __fmul_rn(rm, rm)));
+  } else {
+    out->centre[0] = out->centre[1] = out->centre[2] = 0.0f;
+    out->rmeas = out->tmeas = out->comb = 0.0f;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+prep_kernel(srcv_shape s, srcv_cameras cams, srcv_planes pl, const float* __restrict__ src,
+            float* __restrict__ planes_ws, ViewParams* __restrict__ views,
+            FrameParams* __restrict__ frames, float* __restrict__ src_nhwc) {
+  const long long nv = (long long)s.B * s.K;
+  const long long nf = s.B;
+  const long long np = (pl.mode == SRCV_PLANES_FROM_RANGE) ? (long long)s.B * s.D : 0;
+  const long long HW = (long long)s.H * s.W;
+  const long long nt = src_nhwc ? nv * HW : 0;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nt) {
+    // NCHW -> NHWC: thread = one texel.  Reads are coalesced across the warp
+    // (consecutive pixels of one channel plane); each thread writes its C floats
+    // contiguously.
+    const long long bk = i / HW, p = i - bk * HW;
+    const float* in = src + bk * s.C * HW + p;
+    float* out = src_nhwc + i * s.C;
+    if ((s.C & 3) == 0) {
+      for (int c = 0; c < s.C; c += 4) {
+        float4 v;
+        v.x = __ldg(in + (c + 0) * HW);
+        v.y = __ldg(in + (c + 1) * HW);
+        v.z = __ldg(in + (c + 2) * HW);
+        v.w = __ldg(in + (c + 3) * HW);
+        *reinterpret_cast<float4*>(out + c) = v;
+      }
+    } else {
+      for (int c = 0; c < s.C; ++c) out[c] = __ldg(in + c * HW);
+    }
+    return;
+  }
+  i -= nt;
+  if (i < nv) {
+    const long long b = i / s.K;
+    view_params(cams.src_Ks + i * 16, cams.src_extrinsics + i * 16, cams.cur_invK + b * 16,
+                cams.src_poses ? cams.src_poses + i * 16 : nullptr, views + i);
+    return;
+  }
+  i -= nv;
+  if (i < nf) {
+    const float* invK = cams.cur_invK + i * 16;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) frames[i].invK[r * 3 + c] = invK[r * 4 + c];
+    return;
+  }
+  i -= nf;
+  if (i < np) {
+    const int d = (int)(i % s.D);
+    const float mn = *pl.min_depth, mx = *pl.max_depth;
+    // exp(log(min) + log(max/min) * ramp): three separate torch ops in the reference
+    const float v = expf(__fadd_rn(logf(mn), __fmul_rn(logf(__fdiv_rn(mx, mn)), pl.ramp[d])));
+    planes_ws[i] = v;
+    if (pl.planes_out) pl.planes_out[i] = v;
+  }
+}
+
+template <bool PER_PIXEL>
+__global__ void __launch_bounds__(256)
+argmax_kernel(srcv_shape s, const float* __restrict__ cost, const float* __restrict__ planes,
+              float* __restrict__ lowest) {
+  const long long HW = (long long)s.H * s.W;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)s.B * HW) return;
+  const long long b = i / HW, p = i - b * HW;
+  const float* c = cost + b * s.D * HW + p;
+  float best = 0.f;
+  int best_i = 0;
+  for (int d = 0; d < s.D; ++d) {
+    const float v = __ldg(c + (long long)d * HW);
+    const bool take = (d == 0) || (v > best) || ((v != v) && (best == best));
+    if (take) { best = v; best_i = d; }
+  }
+  lowest[i] = PER_PIXEL ? planes[(b * s.D + best_i) * HW + p] : planes[b * s.D + best_i];
+}
+
+}  // namespace
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+Workspace carve_workspace(const srcv_shape& s, void* base, bool want_nhwc, size_t extra_bytes) {
+  Workspace ws{};
+  size_t off = 0;
+  char* p = static_cast<char*>(base);
+  auto take = [&](size_t bytes) -> char* {
+    char* r = p ? p + off : nullptr;
+    off += align256(bytes);
+    return r;
+  };
+  ws.planes = reinterpret_cast<float*>(take(sizeof(float) * (size_t)s.B * s.D));
+  ws.views = reinterpret_cast<ViewParams*>(take(sizeof(ViewParams) * (size_t)s.B * s.K));
+  ws.frames = reinterpret_cast<FrameParams*>(take(sizeof(FrameParams) * (size_t)s.B));
+  if (want_nhwc) {
+    ws.src_nhwc = reinterpret_cast<float*>(
+        take(sizeof(float) * (size_t)s.B * s.K * s.C * s.H * s.W));
+  }
+  if (extra_bytes) ws.extra = reinterpret_cast<float*>(take(extra_bytes));
+  ws.bytes = off;
+  if (!p) { ws.planes = nullptr; ws.views = nullptr; ws.frames = nullptr; ws.src_nhwc = nullptr; ws.extra = nullptr; }
+  return ws;
+}
+
+cudaError_t launch_prep(const srcv_shape& s, const srcv_cameras& cams, const srcv_planes& pl,
+                        const float* src_feats, const Workspace& ws, bool need_poses,
+                        cudaStream_t stream) {
+  srcv_cameras c = cams;
+  if (!need_poses) c.src_poses = nullptr;
+  const long long nv = (long long)s.B * s.K;
+  const long long np = (pl.mode == SRCV_PLANES_FROM_RANGE) ? (long long)s.B * s.D : 0;
+  const long long nt = ws.src_nhwc ? nv * s.H * s.W : 0;
+  const long long total = nt + nv + s.B + np;
+  const int threads = 256;
+  const long long blocks = (total + threads - 1) / threads;
+  prep_kernel<<<(unsigned)blocks, threads, 0, stream>>>(s, c, pl, src_feats, ws.planes, ws.views,
+                                                        ws.frames, ws.src_nhwc);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_argmax(const srcv_shape& s, const float* cost, const float* planes,
+                          bool per_pixel, float* lowest, cudaStream_t stream) {
+  const long long n = (long long)s.B * s.H * s.W;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  if (per_pixel) argmax_kernel<true><<<blocks, threads, 0, stream>>>(s, cost, planes, lowest);
+  else argmax_kernel<false><<<blocks, threads, 0, stream>>>(s, cost, planes, lowest);
+  note_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace srcv

@@ -1,0 +1,235 @@
+"""GPU parity: the sm_100a kernels (through the C ABI, via the manager classes)
+against (1) the committed golden vectors of the unmodified reference, (2) the CPU
+oracle on seeded inputs, (3) size-independent properties at BASELINE.json's full
+sizes.  Tolerances are stated in tests/parity.py."""
+import pytest
+import torch
+
+import simplerecon_b200 as S
+from oracle import costvolume_oracle as O
+from simplerecon_b200 import _native
+from simplerecon_b200.synthetic import CONFIGS, make_tuple, make_workload_tuple, mlp_state, to_device
+from tests.parity import (assert_cost_close, assert_lowest_close, assert_mask_close, cost_tol,
+                          golden_names, load_golden)
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = {"generic": _native.VARIANT_GENERIC, "fast": _native.VARIANT_FAST, "auto": _native.VARIANT_AUTO}
+
+
+@pytest.fixture(autouse=True)
+def _reset_variant(cuda_device):
+    yield
+    _native.set_variant(_native.VARIANT_AUTO)
+
+
+def make_manager(kind, K, C, H, W, D, sd=None, device="cuda", fast_cls=False):
+    if kind == "dot":
+        m = S.CostVolumeManager(H, W, num_depth_bins=D)
+    else:
+        cls = S.FastFeatureVolumeManager if fast_cls else S.FeatureVolumeManager
+        m = cls(H, W, num_depth_bins=D, mlp_channels=[0, 128, 128, 1], matching_dim_size=C,
+                num_source_views=K)
+        m.load_state_dict({**m.state_dict(), **sd})
+    return m.to(device).eval()
+
+
+def run_gpu(kind, inputs, D, sd=None, variant="auto", return_mask=True, fast_cls=False):
+    B, K, C, H, W = inputs["src_feats"].shape
+    m = make_manager(kind, K, C, H, W, D, sd, fast_cls=fast_cls)
+    _native.set_variant(VARIANTS[variant])
+    with torch.inference_mode():
+        out = m(**to_device(inputs, "cuda"), return_mask=return_mask)
+    torch.cuda.synchronize()
+    return out, _native.last_variant()
+
+
+def fast_ok(kind, inputs):
+    B, K, C, H, W = inputs["src_feats"].shape
+    return kind == "dot" and C == 16 and K <= 8
+
+
+# --------------------------------------------------------------------------- #
+# 1. golden vectors of the unmodified reference                               #
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("variant", ["generic", "fast"])
+@pytest.mark.parametrize("name", golden_names())
+def test_golden(name, variant):
+    g, inputs, sd = load_golden(name)
+    kind = g["kind"]
+    if variant == "fast" and not fast_ok(kind, inputs):
+        pytest.skip("fast variant does not cover this shape")
+    (cost, lowest, planes, mask), used = run_gpu(kind, inputs, g["D"], sd, variant)
+    assert ("fast" in used) == (variant == "fast"), used
+    assert cost.is_contiguous() and cost.dtype == torch.float32 and cost.is_cuda
+    assert_cost_close(kind, cost, g["ref_cost"], g["ref_cost64"], what=f"{name}/{variant}")
+    ref_planes = g["ref_planes"]
+    if ref_planes.dim() == 2:
+        assert planes.stride()[2:] == (0, 0)                       # expanded view, like the reference
+        assert torch.allclose(planes[:, :, 0, 0].cpu(), ref_planes, rtol=3e-7, atol=0)
+    else:
+        assert torch.equal(planes.cpu(), ref_planes)               # caller-supplied planes are handed back
+    assert_lowest_close(kind, lowest, planes, g["ref_cost"], what=name)
+    if kind == "mlp":
+        assert_mask_close(mask, g["ref_mask"], what=name)
+    else:
+        assert mask is None
+
+
+# --------------------------------------------------------------------------- #
+# 2. CPU oracle on seeded inputs                                              #
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("variant", ["generic", "fast"])
+@pytest.mark.parametrize("B,K,H,W,D,seed,smooth", [
+    (2, 7, 60, 80, 32, 3, False),
+    (1, 2, 48, 64, 16, 1234, False),
+    (3, 5, 33, 47, 9, 8, True),        # odd sizes: partial warps and tiles
+    (1, 8, 17, 160, 4, 9, False),
+])
+def test_dot_vs_oracle(B, K, H, W, D, seed, smooth, variant):
+    t = make_tuple(B, K, H, W, seed=seed, smooth=smooth)
+    (cost, lowest, planes, mask), used = run_gpu("dot", t, D, variant=variant)
+    oc, ol, op, _ = O.forward_dot(**t, num_depth_bins=D)
+    assert_cost_close("dot", cost, oc, what=f"dot {used}")
+    assert torch.allclose(planes.cpu()[:, :, 0, 0], op[:, :, 0, 0], rtol=3e-7)
+    assert_lowest_close("dot", lowest, planes, oc, what="dot")
+    assert mask is None
+
+
+@pytest.mark.parametrize("B,K,C,H,W,D,seed", [
+    (1, 7, 16, 30, 40, 16, 5),
+    (2, 3, 16, 21, 19, 5, 6),
+    (1, 2, 8, 16, 24, 4, 7),           # C != 16
+])
+def test_mlp_vs_oracle(B, K, C, H, W, D, seed):
+    t = make_tuple(B, K, H, W, channels=C, seed=seed)
+    sd = mlp_state(K, C, seed=seed)
+    (cost, lowest, planes, mask), used = run_gpu("mlp", t, D, sd)
+    w = O.mlp_weights_from_state_dict(sd)
+    oc, ol, op, om = O.forward_mlp(**t, weights=w, num_depth_bins=D, return_mask=True)
+    assert_cost_close("mlp", cost, oc, what=f"mlp {used}")
+    assert_mask_close(mask, om)
+    # without return_mask the mask is None, like the reference
+    (c2, _, _, m2), _ = run_gpu("mlp", t, D, sd, return_mask=False)
+    assert m2 is None and torch.equal(c2, cost)
+
+
+def test_mlp_other_hidden_widths():
+    # reference API allows any mlp_channels list; widths <= 128 run on the generic kernel
+    t = make_tuple(1, 3, 12, 16, seed=21)
+    m = S.FeatureVolumeManager(12, 16, 4, mlp_channels=[0, 64, 24, 1], matching_dim_size=16,
+                               num_source_views=3).cuda().eval()
+    with torch.inference_mode():
+        cost, lowest, planes, mask = m(**to_device(t, "cuda"), return_mask=True)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    oc, *_ = O.forward_mlp(**t, weights=O.mlp_weights_from_state_dict(sd), num_depth_bins=4, return_mask=True)
+    assert_cost_close("mlp", cost, oc)
+
+
+# --------------------------------------------------------------------------- #
+# 3. BASELINE.json full sizes: properties + one frame against the oracle      #
+# --------------------------------------------------------------------------- #
+def test_full_size_dot_cfg1():
+    w = CONFIGS[1]
+    t = make_workload_tuple(w)
+    (cost, lowest, planes, _), used = run_gpu("dot", t, w.planes, variant="auto")
+    assert "fast" in used and cost.shape == (4, 64, 120, 160)
+    # (a) frame 0 against the CPU oracle at full size
+    t0 = {k: (v[:1] if v.dim() > 0 and v.shape[0] == w.batch else v) for k, v in t.items()}
+    oc, ol, op, _ = O.forward_dot(**t0, num_depth_bins=w.planes)
+    assert_cost_close("dot", cost[:1], oc, what="cfg1 frame0")
+    # (b) both variants agree
+    (cost_g, lowest_g, _, _), _ = run_gpu("dot", t, w.planes, variant="generic")
+    assert (cost - cost_g).abs().max().item() <= cost_tol("dot", oc)
+    # (c) shard invariance: frames 2..3 alone == the same frames inside the batch (bit-exact)
+    th = {k: (v[2:] if v.dim() > 0 and v.shape[0] == w.batch else v) for k, v in t.items()}
+    (cost_h, lowest_h, _, _), _ = run_gpu("dot", th, w.planes)
+    assert torch.equal(cost_h, cost[2:]) and torch.equal(lowest_h, lowest[2:])
+    # (d) homogeneity: scaling the reference features by 2 scales the volume by exactly 2
+    t2 = dict(t); t2["cur_feats"] = t["cur_feats"] * 2
+    (cost2, lowest2, _, _), _ = run_gpu("dot", t2, w.planes)
+    assert torch.equal(cost2, cost * 2) and torch.equal(lowest2, lowest)
+    # (e) lowest_cost is the plane at the argmax of our own volume
+    idx = cost.argmax(1, keepdim=True)
+    assert torch.equal(torch.gather(planes.expand_as(cost), 1, idx).squeeze(1), lowest)
+    # (f) determinism
+    (cost_r, _, _, _), _ = run_gpu("dot", t, w.planes)
+    assert torch.equal(cost_r, cost)
+
+
+def test_full_size_hero_cfg2_two_frames():
+    w = CONFIGS[2]
+    t = make_workload_tuple(w, batch=2)
+    sd = mlp_state(7, 16, seed=0)
+    (cost, lowest, planes, mask), used = run_gpu("mlp", t, w.planes, sd)
+    assert cost.shape == (2, 64, 120, 160) and mask.shape == (2, 120, 160) and mask.dtype == torch.bool
+    t0 = {k: (v[:1] if v.dim() > 0 and v.shape[0] == 2 else v) for k, v in t.items()}
+    oc, ol, op, om = O.forward_mlp(**t0, weights=O.mlp_weights_from_state_dict(sd),
+                                   num_depth_bins=w.planes, return_mask=True)
+    assert_cost_close("mlp", cost[:1], oc, what="cfg2 frame0")
+    assert_mask_close(mask[:1], om)
+    # shard invariance + argmax consistency + the fast class runs the same sweep
+    t1 = {k: (v[1:] if v.dim() > 0 and v.shape[0] == 2 else v) for k, v in t.items()}
+    (cost1, lowest1, _, mask1), _ = run_gpu("mlp", t1, w.planes, sd)
+    assert torch.equal(cost1, cost[1:]) and torch.equal(mask1, mask[1:])
+    idx = cost.argmax(1, keepdim=True)
+    assert torch.equal(torch.gather(planes.expand_as(cost), 1, idx).squeeze(1), lowest)
+    (cost_f, _, _, mask_f), _ = run_gpu("mlp", t, w.planes, sd, fast_cls=True)
+    assert torch.equal(cost_f, cost) and torch.equal(mask_f, mask)
+
+
+# --------------------------------------------------------------------------- #
+# 4. interface behaviour on the device                                        #
+# --------------------------------------------------------------------------- #
+def test_interface_contract_on_device():
+    t = make_tuple(2, 3, 12, 16, seed=31)
+    d = to_device(t, "cuda")
+    m = make_manager("dot", 3, 16, 12, 16, 6)
+    with torch.no_grad():
+        cost, lowest, planes, mask = m(**d)
+        c3, p3, m3 = m.build_cost_volume(**d)
+    assert cost.shape == (2, 6, 12, 16) and lowest.shape == (2, 12, 16) and planes.shape == (2, 6, 12, 16)
+    assert mask is None and m3 is None and torch.equal(c3, cost) and torch.equal(p3, planes)
+    # planes equal what generate_depth_planes (plain torch ops, as in the reference) gives
+    gen = m.generate_depth_planes(2, d["min_depth"], d["max_depth"])
+    assert torch.allclose(planes, gen, rtol=3e-7, atol=0)
+    # caller-supplied expanded planes take the per-plane path and give the same volume
+    with torch.no_grad():
+        cost_p, _, planes_p, _ = m(**d, depth_planes_bdhw=planes)
+    assert planes_p is planes and torch.equal(cost_p, cost)
+    # a non-default stream is honoured
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s), torch.no_grad():
+        cost_s, *_ = m(**d)
+    s.synchronize()
+    assert torch.equal(cost_s, cost)
+    # non-contiguous features are accepted
+    d2 = dict(d); d2["cur_feats"] = d["cur_feats"].permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    with torch.no_grad():
+        cost_nc, *_ = m(**d2)
+    assert torch.equal(cost_nc, cost)
+
+
+def test_errors_on_device():
+    t = to_device(make_tuple(1, 2, 12, 16, seed=32), "cuda")
+    m = make_manager("dot", 2, 16, 12, 16, 4)
+    with torch.no_grad():
+        with pytest.raises(ValueError):
+            S.CostVolumeManager(10, 16, 4).cuda()(**t)                      # wrong H
+        bad = dict(t); bad["src_feats"] = t["src_feats"].half()
+        with pytest.raises(ValueError):
+            m(**bad)
+        bad = dict(t); bad["src_Ks"] = t["src_Ks"][:, :1]
+        with pytest.raises(ValueError):
+            m(**bad)
+    need = dict(t); need["cur_feats"] = t["cur_feats"].clone().requires_grad_(True)
+    with pytest.raises(NotImplementedError):
+        m(**need)
+    # MLP input width inconsistent with K, C
+    f = S.FeatureVolumeManager(12, 16, 4, matching_dim_size=16, num_source_views=7).cuda()
+    with torch.no_grad(), pytest.raises(ValueError):
+        f(**t)
+    _native.set_variant(_native.VARIANT_FAST)
+    t8 = to_device(make_tuple(1, 2, 12, 16, channels=8, seed=33), "cuda")
+    with torch.no_grad(), pytest.raises(_native.SrcvError):
+        m(**t8)
