@@ -5,11 +5,22 @@
 //   Project3D.forward          utils/geometry_utils.py:72-89  (eps 1e-8)
 //   uv normalisation           modules/cost_volume.py:199, :587
 //   F.grid_sample(bilinear, zeros, align_corners=False)  modules/cost_volume.py:201-212
-// re-associated the B200 way: the depth-invariant part of the projection,
+// re-associated the B200 way.  The depth-invariant part of the projection,
 //   Hm = (K E)[:3,:3] invK[:3,:3]   and   t = (K E)[:3,3],
-// is folded once per (frame, view) by the prep kernel (fp64, rounded once), so a
-// plane hypothesis d at pixel centre p projects with three FMAs,  c = d (Hm p) + t,
-// i.e. the plane-induced homography of the sweep.
+// is folded once per (frame, view) by the prep kernel in fp64, so a plane hypothesis d
+// at pixel centre p projects with three FMAs,  c = d (Hm p) + t  — the plane-induced
+// homography of the sweep.
+//
+// Precision: everything is evaluated in *centred* pixel coordinates.  The input
+// pixel is taken relative to the image centre (exact in fp32) and the projected
+// coordinate relative to (floor(W/2)+0.5, floor(H/2)+0.5), i.e. the prep kernel
+// folds   c'_x = c_x - cxo c_z   into Hm and t.  In exact arithmetic the sample
+// index of grid_sample (align_corners=False, after the reference's 2 p / W - 1
+// normalisation) is  i_x = p_x - 0.5 = p'_x + floor(W/2), so floor() and the
+// bilinear fraction are taken on p' (|p'| <= W/2: half the ulp of the reference's
+// un-centred chain, and no normalise/unnormalise round trip).  Measured against the
+// fp64 evaluation of the reference this is closer than the reference's own fp32
+// result ("numerics").
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -23,8 +34,10 @@ constexpr float kLeaky = 0.01f;     // nn.LeakyReLU default slope
 
 // Per (frame b, view k) constants, written by prep_kernel.  32 floats = 128 B.
 struct ViewParams {
-  float Hm[9];     // (K E)[:3,:3] @ invK[:3,:3], row-major
-  float t[3];      // (K E)[:3,3]
+  float a0[3];     // centred homography applied to the image centre
+  float hx[3];     // d a'/d dx  (column 0 of the centred Hm)
+  float hy[3];     // d a'/d dy  (column 1)
+  float t[3];      // centred translation
   float centre[3]; // src_poses[:3,3]: source camera centre in the reference frame
   float comb;      // pose_distance: sqrt(t_meas^2 + r_meas^2)
   float rmeas;     // sqrt(2 (1 - min(3, tr R)/3))
@@ -32,6 +45,7 @@ struct ViewParams {
   float pad[14];
 };
 static_assert(sizeof(ViewParams) == 128, "ViewParams must be 128 bytes");
+constexpr int kViewFloats = 12;  // a0, hx, hy, t: what the sweep kernels stage in smem
 
 // Per frame constants: invK[:3,:3] (row-major) for the ray r = invK3 p.
 struct FrameParams {
@@ -40,18 +54,23 @@ struct FrameParams {
 };
 static_assert(sizeof(FrameParams) == 64, "FrameParams must be 64 bytes");
 
-// Bilinear footprint of one projected sample.
-struct Taps {
-  int x0, y0;        // top-left texel (may be out of range)
-  float w[4];        // nw, ne, sw, se weights, already zeroed for invalid taps
-                     // and for points behind the camera when `fold_mask`
-  unsigned valid;    // bit0 nw, bit1 ne, bit2 sw, bit3 se in-bounds
-  float zp;          // z' = z + eps   (the depth channel the reference returns)
-  float px, py;      // projected pixel coordinates
+// Image-size constants of the centred frame.
+struct Centre {
+  float half_w, half_h;  // W/2, H/2: input centre (pixel centres are u+0.5)
+  int nx, ny;            // floor(W/2), floor(H/2): integer part of the output offset
+  __host__ __device__ Centre(int W, int H)
+      : half_w(0.5f * (float)W), half_h(0.5f * (float)H), nx(W / 2), ny(H / 2) {}
 };
 
-// c = d * a + t, guarded divide (geometry_utils.py:83-89), grid normalisation
-// (cost_volume.py:199) and ATen's unnormalise for align_corners=False.
+// a' = a0 + hx dx + hy dy  for pixel (u, v)
+__device__ __forceinline__ void homography_point(const float* __restrict__ vp, float dx, float dy,
+                                                 float& ax, float& ay, float& az) {
+  ax = fmaf(vp[3], dx, fmaf(vp[6], dy, vp[0]));
+  ay = fmaf(vp[4], dx, fmaf(vp[7], dy, vp[1]));
+  az = fmaf(vp[5], dx, fmaf(vp[8], dy, vp[2]));
+}
+
+// c' = d a' + t', guarded divide (geometry_utils.py:83-89).  px, py are CENTRED.
 __device__ __forceinline__ void project_point(float d, float ax, float ay, float az,
                                               float tx, float ty, float tz,
                                               float& px, float& py, float& zp) {
@@ -60,38 +79,40 @@ __device__ __forceinline__ void project_point(float d, float ax, float ay, float
   const float z = fmaf(d, az, tz);
   zp = __fadd_rn(z, kEpsProj);
   const float s = (fabsf(z) > kEpsProj) ? __frcp_rn(zp) : 1.0f;
-  px = __fmul_rn(cx, s);
-  py = __fmul_rn(cy, s);
+  px = cx * s;
+  py = cy * s;
 }
 
-__device__ __forceinline__ void bilinear_taps(float px, float py, int W, int H,
-                                              float inv_w, float inv_h, Taps& tp) {
-  // g = 2*p*(1/size) - 1 ; i = ((g + 1)*size - 1)/2   (separate roundings, as torch)
-  const float gx = __fadd_rn(__fmul_rn(__fmul_rn(2.0f, px), inv_w), -1.0f);
-  const float gy = __fadd_rn(__fmul_rn(__fmul_rn(2.0f, py), inv_h), -1.0f);
-  const float ix = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(gx, 1.0f), (float)W), -1.0f), 0.5f);
-  const float iy = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(gy, 1.0f), (float)H), -1.0f), 0.5f);
-  const float x0f = floorf(ix), y0f = floorf(iy);
-  const float x1f = x0f + 1.0f, y1f = y0f + 1.0f;
-  const float wx1 = ix - x0f, wx0 = x1f - ix;
-  const float wy1 = iy - y0f, wy0 = y1f - iy;
-  // in-bounds tests in float first: NaN and huge coordinates fail all of them
-  const bool xa = (x0f >= 0.0f) && (x0f <= (float)(W - 1));
-  const bool xb = (x1f >= 0.0f) && (x1f <= (float)(W - 1));
-  const bool ya = (y0f >= 0.0f) && (y0f <= (float)(H - 1));
-  const bool yb = (y1f >= 0.0f) && (y1f <= (float)(H - 1));
-  const bool any = (xa || xb) && (ya || yb);
-  // when no tap is valid the integer coordinates are never used; pin them
-  tp.x0 = any ? (int)x0f : 0;
-  tp.y0 = any ? (int)y0f : 0;
-  tp.valid = (unsigned)(xa && ya) | ((unsigned)(xb && ya) << 1) |
-             ((unsigned)(xa && yb) << 2) | ((unsigned)(xb && yb) << 3);
-  tp.w[0] = (xa && ya) ? wx0 * wy0 : 0.0f;
-  tp.w[1] = (xb && ya) ? wx1 * wy0 : 0.0f;
-  tp.w[2] = (xa && yb) ? wx0 * wy1 : 0.0f;
-  tp.w[3] = (xb && yb) ? wx1 * wy1 : 0.0f;
-  tp.px = px;
-  tp.py = py;
+// Bilinear footprint of one projected sample (centred coordinates in).
+struct Taps {
+  int x0, y0;      // top-left texel (may be out of range by one)
+  float fx, fy;    // fractions: weights are (1-fx|fx) x (1-fy|fy)
+  unsigned valid;  // bit0 nw, bit1 ne, bit2 sw, bit3 se in-bounds (zeros padding otherwise)
+};
+
+__device__ __forceinline__ void bilinear_taps(float px, float py, int W, int H, const Centre& c,
+                                              Taps& tp) {
+  const float x0f = floorf(px), y0f = floorf(py);
+  tp.fx = px - x0f;
+  tp.fy = py - y0f;
+  // NaN / inf / absurd coordinates sample nothing (all four taps are padding)
+  const bool finite = (fabsf(px) < 1.0e6f) && (fabsf(py) < 1.0e6f);
+  const int x0 = finite ? (int)x0f + c.nx : -2;
+  const int y0 = finite ? (int)y0f + c.ny : -2;
+  const bool xa = (unsigned)x0 < (unsigned)W, xb = (unsigned)(x0 + 1) < (unsigned)W;
+  const bool ya = (unsigned)y0 < (unsigned)H, yb = (unsigned)(y0 + 1) < (unsigned)H;
+  tp.valid = (unsigned)(xa && ya) | ((unsigned)(xb && ya) << 1) | ((unsigned)(xa && yb) << 2) |
+             ((unsigned)(xb && yb) << 3);
+  const bool any = tp.valid != 0u;
+  tp.x0 = any ? x0 : 0;
+  tp.y0 = any ? y0 : 0;
+}
+
+// Bounds test of CostVolumeManager.get_mask (modules/cost_volume.py:90-95) on
+// centred coordinates: 2 < p < size - 2.
+__device__ __forceinline__ bool in_mask_bounds(float px, float py, int W, int H, const Centre& c) {
+  const float ox = (float)c.nx + 0.5f, oy = (float)c.ny + 0.5f;
+  return px > 2.0f - ox && px < (float)(W - 2) - ox && py > 2.0f - oy && py < (float)(H - 2) - oy;
 }
 
 __device__ __forceinline__ float leaky(float x) { return x > 0.0f ? x : kLeaky * x; }

@@ -118,7 +118,7 @@ mlp_generic_kernel(srcv_shape s, MlpDims m, const float* __restrict__ cur,
   const int o_cur = K * C, o_mask = o_cur + C, o_z = o_mask + K, o_depth = o_z + K,
             o_dot = o_depth + 1, o_ang = o_dot + K, o_ncur = o_ang + K, o_nsrc = o_ncur + 3,
             o_comb = o_nsrc + 3 * K, o_r = o_comb + K, o_t = o_r + K;
-  const float inv_w = 1.0f / (float)s.W, inv_h = 1.0f / (float)s.H;
+  const Centre ctr(s.W, s.H);
   const FrameParams fp = frames[b];
 
   if (tid < TM) sFlag[tid] = 0;
@@ -132,13 +132,13 @@ mlp_generic_kernel(srcv_shape s, MlpDims m, const float* __restrict__ cur,
     const float dval = PER_PIXEL ? __ldg(planes + ((size_t)b * s.D + d) * HW + p)
                                  : __ldg(planes + b * s.D + d);
     const ViewParams& vp = views[b * K + k];
-    const float ax = fmaf(vp.Hm[0], pxc, fmaf(vp.Hm[1], pyc, vp.Hm[2]));
-    const float ay = fmaf(vp.Hm[3], pxc, fmaf(vp.Hm[4], pyc, vp.Hm[5]));
-    const float az = fmaf(vp.Hm[6], pxc, fmaf(vp.Hm[7], pyc, vp.Hm[8]));
-    float px, py, zp;
+    float ax, ay, az, px, py, zp;
+    homography_point(vp.a0, pxc - ctr.half_w, pyc - ctr.half_h, ax, ay, az);
     project_point(dval, ax, ay, az, vp.t[0], vp.t[1], vp.t[2], px, py, zp);
     Taps tp;
-    bilinear_taps(px, py, s.W, s.H, inv_w, inv_h, tp);
+    bilinear_taps(px, py, s.W, s.H, ctr, tp);
+    const float w00 = (1.0f - tp.fx) * (1.0f - tp.fy), w01 = tp.fx * (1.0f - tp.fy);
+    const float w10 = (1.0f - tp.fx) * tp.fy, w11 = tp.fx * tp.fy;
     const float mk = zp > 0.0f ? 1.0f : 0.0f;
     // warped features + per-view dot (features are sampled even behind the camera,
     // reference modules/cost_volume.py:590-623: only the dot is masked)
@@ -148,10 +148,10 @@ mlp_generic_kernel(srcv_shape s, MlpDims m, const float* __restrict__ cur,
     for (int c = 0; c < C; ++c) {
       const float* q = sp + (size_t)c * HW;
       float v = 0.f;
-      if (tp.valid & 1u) v = tp.w[0] * __ldg(q);
-      if (tp.valid & 2u) v = fmaf(tp.w[1], __ldg(q + 1), v);
-      if (tp.valid & 4u) v = fmaf(tp.w[2], __ldg(q + s.W), v);
-      if (tp.valid & 8u) v = fmaf(tp.w[3], __ldg(q + s.W + 1), v);
+      if (tp.valid & 1u) v = w00 * __ldg(q);
+      if (tp.valid & 2u) v = fmaf(w01, __ldg(q + 1), v);
+      if (tp.valid & 4u) v = fmaf(w10, __ldg(q + s.W), v);
+      if (tp.valid & 8u) v = fmaf(w11, __ldg(q + s.W + 1), v);
       sA[(k * C + c) * TM + r] = v;
       dot = fmaf(v, __ldg(cp + (size_t)c * HW), dot);
     }
@@ -190,7 +190,7 @@ mlp_generic_kernel(srcv_shape s, MlpDims m, const float* __restrict__ cur,
     if (want_mask) {
       int bits = 0;
       if (zp > 0.0f) bits |= 1;
-      if (px > 2.0f && px < (float)(s.W - 2) && py > 2.0f && py < (float)(s.H - 2)) bits |= 2;
+      if (in_mask_bounds(px, py, s.W, s.H, ctr)) bits |= 2;
       if (bits) atomicOr(&sFlag[r], bits);
     }
   }

@@ -17,9 +17,9 @@ namespace {
 
 __device__ void view_params(const float* __restrict__ Kmat, const float* __restrict__ E,
                             const float* __restrict__ invK, const float* __restrict__ pose,
-                            ViewParams* out) {
-  // P = K @ E (rows 0..2), fp64 then one rounding.
-  double P[3][4];
+                            int W, int H, ViewParams* out) {
+  // P = K @ E (rows 0..2) and Hm = P[:, :3] @ invK[:3, :3], fp64, rounded once at the end.
+  double P[3][4], Hm[3][3];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -30,16 +30,31 @@ __device__ void view_params(const float* __restrict__ Kmat, const float* __restr
       P[i][j] = a;
     }
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       double a = 0.0;
 #pragma unroll
       for (int l = 0; l < 3; ++l) a += P[i][l] * (double)invK[l * 4 + j];
-      out->Hm[i * 3 + j] = (float)a;
+      Hm[i][j] = a;
     }
-    out->t[i] = (float)P[i][3];
+  // centre the OUTPUT: c'_x = c_x - cxo c_z, c'_y = c_y - cyo c_z  (see srcv_common.cuh)
+  const double cxo = (double)(W / 2) + 0.5, cyo = (double)(H / 2) + 0.5;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    Hm[0][j] -= cxo * Hm[2][j];
+    Hm[1][j] -= cyo * Hm[2][j];
   }
+  const double tx = P[0][3] - cxo * P[2][3], ty = P[1][3] - cyo * P[2][3], tz = P[2][3];
+  // centre the INPUT: p = (W/2 + dx, H/2 + dy, 1)
+  const double ux = 0.5 * (double)W, uy = 0.5 * (double)H;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    out->a0[i] = (float)(Hm[i][0] * ux + Hm[i][1] * uy + Hm[i][2]);
+    out->hx[i] = (float)Hm[i][0];
+    out->hy[i] = (float)Hm[i][1];
+  }
+  out->t[0] = (float)tx; out->t[1] = (float)ty; out->t[2] = (float)tz;
   if (pose != nullptr) {
     const float t0 = pose[3], t1 = pose[7], t2 = pose[11];
     out->centre[0] = t0; out->centre[1] = t1; out->centre[2] = t2;
@@ -91,7 +106,7 @@ prep_kernel(srcv_shape s, srcv_cameras cams, srcv_planes pl, const float* __rest
   if (i < nv) {
     const long long b = i / s.K;
     view_params(cams.src_Ks + i * 16, cams.src_extrinsics + i * 16, cams.cur_invK + b * 16,
-                cams.src_poses ? cams.src_poses + i * 16 : nullptr, views + i);
+                cams.src_poses ? cams.src_poses + i * 16 : nullptr, s.W, s.H, views + i);
     return;
   }
   i -= nv;

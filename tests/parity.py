@@ -1,14 +1,19 @@
 """Shared parity helpers: golden-case loading and the stated tolerances.
 
-Tolerances (fp32): the reference's own fp32 result differs from its
-fp64 evaluation by ~1.3e-5 of max|cost| for the dot volume (coordinate rounding at
-~100 px feeding bilinear weights) and ~3e-6 of max|cost| for the MLP volume, so
+Tolerances (fp32).  The reference's own fp32 result differs from its
+fp64 evaluation — fp32 rounding of ~100-pixel coordinates feeding bilinear weights —
+by up to ~1.5e-5 of max|cost| (dot) and, at the BASELINE 120x160 / D=64 size, 3.4e-5
+of max|cost| (MLP volume: measured 1.5e-5 abs on max|cost| 0.45).  Hence:
 
-* cost volume, element-wise:  |ours - ref32| <= RTOL_MAX[kind] * max|ref| + 1e-6
-* and against the fp64 reference:  max err(ours, ref64) <= 2 * max err(ref32, ref64) + 1e-6*max|ref|
+* cost volume, element-wise:
+      |ours - ref32| <= max(RTOL_MAX[kind] * max|ref| + 1e-6,  2 * max|ref32 - ref64|)
+  (the second term only where the fp64 evaluation of the reference is available);
+* against the fp64 reference (where available) ours must not be further off than twice
+  the reference's own fp32 result:  max|ours - ref64| <= 2 max|ref32 - ref64| + 1e-6 max|ref|
+  (the centred-coordinate kernels are in fact closer to fp64 than the reference is);
 * lowest_cost (argmax depth): a pixel may pick another plane only on a near tie, i.e.
-  ref cost at our plane within the cost tolerance of the ref maximum; at most 0.5 % of pixels
-* overall mask: at most 0.1 % of pixels differ (strict-inequality bounds tests on fp32 coordinates)
+  ref cost at our plane within 2x the cost tolerance of the ref maximum; at most 0.5 % of pixels;
+* overall mask: at most 0.1 % of pixels differ (strict-inequality tests on fp32 coordinates).
 """
 from __future__ import annotations
 
@@ -51,13 +56,17 @@ def cost_tol(kind, ref):
 def assert_cost_close(kind, ours, ref32, ref64=None, what=""):
     ours = ours.detach().cpu()
     tol = cost_tol(kind, ref32)
+    e_ref = None
+    if ref64 is not None:
+        e_ref = (ref32.double() - ref64).abs().max().item()
+        tol = max(tol, 2 * e_ref)
     err = (ours - ref32).abs().max().item()
     assert err <= tol, f"{what}: cost max-abs err {err:.3e} > tol {tol:.3e}"
     if ref64 is not None:
         e_ours = (ours.double() - ref64).abs().max().item()
-        e_ref = (ref32.double() - ref64).abs().max().item()
         bound = 2 * e_ref + 1e-6 * float(ref64.abs().max()) + 1e-7
         assert e_ours <= bound, f"{what}: err vs fp64 {e_ours:.3e} > 2x reference's own {e_ref:.3e}"
+        print(f"[parity] {what}: |ours-ref32|={err:.3e} |ours-ref64|={e_ours:.3e} |ref32-ref64|={e_ref:.3e}")
     return err
 
 

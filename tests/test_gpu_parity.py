@@ -137,7 +137,8 @@ def test_full_size_dot_cfg1():
     # (a) frame 0 against the CPU oracle at full size
     t0 = {k: (v[:1] if v.dim() > 0 and v.shape[0] == w.batch else v) for k, v in t.items()}
     oc, ol, op, _ = O.forward_dot(**t0, num_depth_bins=w.planes)
-    assert_cost_close("dot", cost[:1], oc, what="cfg1 frame0")
+    oc64, *_ = O.forward_dot(**{k: v.double() for k, v in t0.items()}, num_depth_bins=w.planes)
+    assert_cost_close("dot", cost[:1], oc, oc64, what="cfg1 frame0")
     # (b) both variants agree
     (cost_g, lowest_g, _, _), _ = run_gpu("dot", t, w.planes, variant="generic")
     assert (cost - cost_g).abs().max().item() <= cost_tol("dot", oc)
@@ -164,9 +165,11 @@ def test_full_size_hero_cfg2_two_frames():
     (cost, lowest, planes, mask), used = run_gpu("mlp", t, w.planes, sd)
     assert cost.shape == (2, 64, 120, 160) and mask.shape == (2, 120, 160) and mask.dtype == torch.bool
     t0 = {k: (v[:1] if v.dim() > 0 and v.shape[0] == 2 else v) for k, v in t.items()}
-    oc, ol, op, om = O.forward_mlp(**t0, weights=O.mlp_weights_from_state_dict(sd),
-                                   num_depth_bins=w.planes, return_mask=True)
-    assert_cost_close("mlp", cost[:1], oc, what="cfg2 frame0")
+    wts = O.mlp_weights_from_state_dict(sd)
+    oc, ol, op, om = O.forward_mlp(**t0, weights=wts, num_depth_bins=w.planes, return_mask=True)
+    oc64, *_ = O.forward_mlp(**{k: v.double() for k, v in t0.items()},
+                             weights=tuple(x.double() for x in wts), num_depth_bins=w.planes)
+    assert_cost_close("mlp", cost[:1], oc, oc64, what="cfg2 frame0")
     assert_mask_close(mask[:1], om)
     # shard invariance + argmax consistency + the fast class runs the same sweep
     t1 = {k: (v[1:] if v.dim() > 0 and v.shape[0] == 2 else v) for k, v in t.items()}
