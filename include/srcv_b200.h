@@ -158,6 +158,13 @@ const char* srcv_last_variant(void);
 uint64_t srcv_launch_count(void);
 
 
+/* ---- tensor-core self-test (test support) -------------------------------- *
+ * D (128,128) = A (128,Kp) W^T, W (128,Kp), all DEVICE fp32, Kp a multiple of 16
+ * and <= 256, through the same TMEM / descriptor / mbarrier machinery as the
+ * metadata-MLP kernel (fp16 hi/lo split, three MMAs).  `scratch` = 512*Kp bytes.  */
+int32_t srcv_tc_selftest_f32(const float* A, const float* W, int32_t Kp, float* D, void* scratch,
+                             void* stream);
+
 /* ---- per-kernel timing (benchmark support) ---------------------------- *
  * Between srcv_profile_begin and srcv_profile_end every forward call records
  * CUDA events on ITS stream around the prep pass and around the sweep kernel(s)

@@ -64,6 +64,7 @@ SYMBOLS = {
     "srcv_set_variant": (C.c_int32, [C.c_int32]),
     "srcv_last_variant": (C.c_char_p, []),
     "srcv_launch_count": (C.c_uint64, []),
+    "srcv_tc_selftest_f32": (C.c_int32, [_fp, _fp, C.c_int32, _fp, _fp, _fp]),
     "srcv_profile_begin": (C.c_int32, [C.c_int32]),
     "srcv_profile_end": (C.c_int32, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
 }

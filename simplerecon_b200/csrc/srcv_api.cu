@@ -152,7 +152,7 @@ int32_t srcv_dot_forward_f32(const srcv_shape* s, const float* cur, const float*
   const Workspace need = carve_workspace(*s, nullptr, dot_fast_supported(*s), 0);
   if (int32_t e = check_workspace(workspace, workspace_bytes, need.bytes)) return e;
   Workspace ws = carve_workspace(*s, workspace, dot_fast_supported(*s), 0);
-  if (!fast) ws.src_nhwc = nullptr;  // skip the channel-last copy
+  if (!fast) ws.src_c4 = nullptr;  // skip the chunk-planar copy
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ProfRecord* pr = prof_next();
   if (pr) cudaEventRecord(pr->e[0], stream);
@@ -162,7 +162,7 @@ int32_t srcv_dot_forward_f32(const srcv_shape* s, const float* cur, const float*
   const bool per_pixel = pl->mode == SRCV_PLANES_PER_PIXEL;
   const float* planes = pl->mode == SRCV_PLANES_FROM_RANGE ? ws.planes : pl->planes;
   if (fast) {
-    g_last_variant = "dot_fast_nhwc_quadlane";
+    g_last_variant = "dot_fast_c4planar";
     err = launch_dot_fast(*s, cur, ws, planes, per_pixel, cost, lowest, stream);
   } else {
     g_last_variant = "dot_generic";
@@ -183,10 +183,21 @@ static int32_t check_weights(const srcv_shape* s, const srcv_mlp_weights* w) {
   return SRCV_OK;
 }
 
+static bool use_tc_mlp(const srcv_shape& s, const srcv_mlp_weights& w) {
+  if (g_variant.load() == SRCV_VARIANT_GENERIC) return false;
+  return mlp_tc_supported(s, w);
+}
+
+static size_t mlp_extra_bytes(const srcv_shape& s, const srcv_mlp_weights& w) {
+  size_t e = mlp_generic_extra_bytes(s, w);
+  if (mlp_tc_supported(s, w) && mlp_tc_extra_bytes() > e) e = mlp_tc_extra_bytes();
+  return e;
+}
+
 size_t srcv_mlp_workspace_bytes(const srcv_shape* s, const srcv_mlp_weights* w) {
   if (check_shape(s) != SRCV_OK || !w) return 0;
   if (!mlp_generic_supported(*s, *w)) return 0;
-  return carve_workspace(*s, nullptr, false, mlp_generic_extra_bytes(*s, *w)).bytes;
+  return carve_workspace(*s, nullptr, mlp_tc_supported(*s, *w), mlp_extra_bytes(*s, *w)).bytes;
 }
 
 int32_t srcv_mlp_forward_f32(const srcv_shape* s, const float* cur, const float* src,
@@ -196,10 +207,15 @@ int32_t srcv_mlp_forward_f32(const srcv_shape* s, const float* cur, const float*
                              void* stream_) {
   if (int32_t e = check_common(s, cur, src, cams, pl, cost, true)) return e;
   if (int32_t e = check_weights(s, w)) return e;
-  const size_t extra = mlp_generic_extra_bytes(*s, *w);
-  const Workspace need = carve_workspace(*s, nullptr, false, extra);
+  const bool tc = use_tc_mlp(*s, *w);
+  if (g_variant.load() == SRCV_VARIANT_FAST && !tc)
+    return fail(SRCV_ERR_UNSUPPORTED, "tensor-core MLP variant needs K == 7, C == 16, hidden widths 128/128");
+  const size_t extra = mlp_extra_bytes(*s, *w);
+  const bool c4 = mlp_tc_supported(*s, *w);
+  const Workspace need = carve_workspace(*s, nullptr, c4, extra);
   if (int32_t e = check_workspace(workspace, workspace_bytes, need.bytes)) return e;
-  Workspace ws = carve_workspace(*s, workspace, false, extra);
+  Workspace ws = carve_workspace(*s, workspace, c4, extra);
+  if (!tc) ws.src_c4 = nullptr;  // skip the chunk-planar copy
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ProfRecord* pr = prof_next();
   if (pr) cudaEventRecord(pr->e[0], stream);
@@ -208,10 +224,23 @@ int32_t srcv_mlp_forward_f32(const srcv_shape* s, const float* cur, const float*
   if (pr) cudaEventRecord(pr->e[1], stream);
   const bool per_pixel = pl->mode == SRCV_PLANES_PER_PIXEL;
   const float* planes = pl->mode == SRCV_PLANES_FROM_RANGE ? ws.planes : pl->planes;
-  g_last_variant = "mlp_generic_fp32";
-  err = launch_mlp_generic(*s, cur, src, ws, planes, per_pixel, *w, cost, lowest, overall_mask, stream);
+  if (tc) {
+    g_last_variant = "mlp_tc_tcgen05_f16x3";
+    err = launch_mlp_tc(*s, cur, ws, planes, per_pixel, *w, cost, lowest, overall_mask, stream);
+  } else {
+    g_last_variant = "mlp_generic_fp32";
+    err = launch_mlp_generic(*s, cur, src, ws, planes, per_pixel, *w, cost, lowest, overall_mask, stream);
+  }
   if (err != cudaSuccess) return cuda_fail(err, g_last_variant);
   if (pr) cudaEventRecord(pr->e[2], stream);
+  return SRCV_OK;
+}
+
+int32_t srcv_tc_selftest_f32(const float* A, const float* Wm, int32_t Kp, float* D, void* scratch,
+                             void* stream) {
+  if (!A || !Wm || !D || !scratch) return fail(SRCV_ERR_NULL, "selftest pointer is NULL");
+  cudaError_t err = launch_tc_selftest(A, Wm, Kp, D, scratch, static_cast<cudaStream_t>(stream));
+  if (err != cudaSuccess) return cuda_fail(err, "tc_selftest");
   return SRCV_OK;
 }
 

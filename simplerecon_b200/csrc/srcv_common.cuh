@@ -78,7 +78,13 @@ __device__ __forceinline__ void project_point(float d, float ax, float ay, float
   const float cy = fmaf(d, ay, ty);
   const float z = fmaf(d, az, tz);
   zp = __fadd_rn(z, kEpsProj);
-  const float s = (fabsf(z) > kEpsProj) ? __frcp_rn(zp) : 1.0f;
+  // 1/z': hardware reciprocal + one Newton step (branch-free, <= 1 ulp) instead of the
+  // IEEE-rounded division's slow path; the residual is far below the pixel-coordinate
+  // rounding that follows.
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(zp));
+  r = fmaf(r, fmaf(-zp, r, 1.0f), r);
+  const float s = (fabsf(z) > kEpsProj) ? r : 1.0f;
   px = cx * s;
   py = cy * s;
 }

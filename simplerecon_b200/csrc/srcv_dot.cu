@@ -9,19 +9,18 @@
 //
 // Two variants:
 //  * generic — any K, C; one thread per pixel, planar (NCHW) scalar gathers.
-//  * fast    — C == 16; gathers from the channel-last copy made by the prep pass.
-//    A warp owns an 8x4 block of pixels (2-D so the bilinear footprints of its
-//    pixels overlap in both directions).  Lane l does the projection of pixel
-//    (l%8, l/8) ("owner" role); for the gather the warp re-partitions itself into 8
-//    groups of 4 lanes: in round r group g serves pixel (g, r) and lane j of the
-//    group loads the 16-byte channel chunk j of each tap, so one warp-wide LDG.128
-//    moves 8 whole 64-byte texels that are contiguous in memory whenever the 8
-//    pixels' taps are (they are for the near-translational homographies of a
-//    keyframe sweep): full 128 B/clk L1 wavefronts instead of 32 scattered 16-byte
-//    pieces.  The sample's footprint travels owner->group by three shuffles and
-//    the partial dots come back the same way.  Loop order is
-//    plane-chunk -> view -> plane-in-chunk, so consecutive samples walk along one
-//    epipolar line of one view and re-hit the lines they just pulled into L1.
+//  * fast    — C == 16; one thread per pixel, a warp owns a 16x2 block of pixels
+//    (2-D so the bilinear footprints overlap in both directions).  It gathers
+//    from the chunk-planar copy made by the prep pass, laid out (B,K,C/4,H,W,4):
+//    the 4-channel chunk of a texel is one 16-byte vector and horizontally
+//    adjacent texels are adjacent in memory, so the warp-wide LDG.128 of a tap
+//    reads two 256-byte row segments: the full-width 128 B/clk L1 access shape
+//    with every lane keeping its own sample (no cross-lane traffic at all, where
+//    a channel-last texel layout needs shuffles to re-partition the warp).  Loop
+//    order is plane-chunk -> view -> plane-in-chunk, so consecutive samples walk
+//    along one epipolar line of one view and re-hit the lines just pulled into L1.
+#include <cstdlib>
+
 #include "srcv_kernels.h"
 
 namespace srcv {
@@ -82,80 +81,94 @@ dot_generic_kernel(srcv_shape s, const float* __restrict__ cur, const float* __r
 }
 
 // --------------------------------------------------------------------------- //
-// fast: C = 16, channel-last gathers, 4 lanes per texel                       //
+// fast: one thread per pixel, gathers from the chunk-planar (B,K,C/4,H,W,4) copy //
 // --------------------------------------------------------------------------- //
 constexpr int kFastC = 16;
-constexpr int kTileW = 8, kTileH = 4;   // pixels per warp
-constexpr int kFastWarps = 2;           // CTA = 8 x 8 pixels
+constexpr int kNChunk = kFastC / 4;
+constexpr int kFastWarps = 2;           // CTA = 16 x 4 pixels
 constexpr int kDC = 4;                  // planes per inner chunk
-constexpr unsigned kFull = 0xffffffffu;
 
-__device__ __forceinline__ float dot4(const float4& v, const float4& c) {
-  return fmaf(v.x, c.x, fmaf(v.y, c.y, fmaf(v.z, c.z, v.w * c.w)));
+__device__ __forceinline__ float dot4(const float4& v, const float4& c, float acc) {
+  return fmaf(v.x, c.x, fmaf(v.y, c.y, fmaf(v.z, c.z, fmaf(v.w, c.w, acc))));
 }
 
-template <bool PER_PIXEL>
+// One bilinear tap: C/4 vector loads at compile-time-constant distances from the
+// sample's base pointer, reduced against the reference features in two chains.
+template <bool PRED, int HWC>
+__device__ __forceinline__ float tap_dot(const float4* __restrict__ q, int hw, bool on,
+                                         const float4 (&cur4)[kNChunk]) {
+  const int stride = HWC ? HWC : hw;
+  float4 v[kNChunk];
+#pragma unroll
+  for (int j = 0; j < kNChunk; ++j) {
+    if (PRED) v[j] = on ? __ldg(q + (size_t)j * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+    else v[j] = __ldg(q + (size_t)j * stride);
+  }
+  float ta = 0.f, tb = 0.f;
+#pragma unroll
+  for (int j = 0; j < kNChunk; j += 2) {
+    ta = dot4(v[j], cur4[j], ta);
+    if (j + 1 < kNChunk) tb = dot4(v[j + 1], cur4[j + 1], tb);
+  }
+  return ta + tb;
+}
+
+// TW, TH: compile-time feature-map size (0 = take it from the shape at run time).
+// With a known size every one of the 16 vector loads of a sample is the sample's
+// base pointer plus an immediate, which removes ~45 integer instructions per sample.
+template <bool PER_PIXEL, int TW, int TH, int kTileW>
 __global__ void __launch_bounds__(kFastWarps * 32)
 dot_fast_kernel(srcv_shape s, const float* __restrict__ cur, const float4* __restrict__ src4,
                 const ViewParams* __restrict__ views, const float* __restrict__ planes,
                 float* __restrict__ cost, float* __restrict__ lowest) {
   extern __shared__ float sview[];  // K * 12
   const int b = blockIdx.y;
-  const int W = s.W, H = s.H, HW = W * H, K = s.K;
+  const int W = TW ? TW : s.W, H = TH ? TH : s.H, HW = W * H, K = s.K;
+  constexpr int HWC = TW * TH;
+  constexpr int kTileH = 32 / kTileW;  // pixels per warp: lane -> (lane % kTileW, lane / kTileW)
   for (int i = threadIdx.x; i < K * kViewFloats; i += blockDim.x)
     sview[i] = reinterpret_cast<const float*>(views + b * K + i / kViewFloats)[i % kViewFloats];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int tiles_x = (W + kTileW - 1) / kTileW;
-  const int x_base = (blockIdx.x % tiles_x) * kTileW;
-  const int y_base = ((blockIdx.x / tiles_x) * kFastWarps + (threadIdx.x >> 5)) * kTileH;
-  if (y_base >= H) return;  // warp-uniform
+  const int ox_raw = (blockIdx.x % tiles_x) * kTileW + (lane & (kTileW - 1));
+  const int oy_raw = ((blockIdx.x / tiles_x) * kFastWarps + (threadIdx.x >> 5)) * kTileH + lane / kTileW;
+  const bool active = ox_raw < W && oy_raw < H;
+  if (__ballot_sync(0xffffffffu, active) == 0u) return;  // whole warp outside the map
+  const int ox = min(ox_raw, W - 1), oy = min(oy_raw, H - 1);  // idle lanes shadow a real pixel
   // planes handled by this CTA: [d_begin, d_end)
   const int dper = (s.D + gridDim.z - 1) / gridDim.z;
   const int d_begin = blockIdx.z * dper;
   const int d_end = min(s.D, d_begin + dper);
   const bool fuse_argmax = (gridDim.z == 1) && (lowest != nullptr);
   const Centre ctr(W, H);
+  const int p = oy * W + ox;
+  const float dx = ((float)ox + 0.5f) - ctr.half_w, dy = ((float)oy + 0.5f) - ctr.half_h;
 
-  // ---- owner role: pixel (lane % 8, lane / 8) of the block -------------------
-  const int ox = x_base + (lane & 7), oy = y_base + (lane >> 3);
-  const bool active = ox < W && oy < H;
-  const int p = min(oy, H - 1) * W + min(ox, W - 1);
-  const float dx = ((float)min(ox, W - 1) + 0.5f) - ctr.half_w;
-  const float dy = ((float)min(oy, H - 1) + 0.5f) - ctr.half_h;
-  // ---- helper role: channel chunk j of pixel (g, r) in round r ----------------
-  const int g = lane >> 2, j = lane & 3;
-  float4 cur4[4];
+  float4 cur4[kNChunk];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int q = min(y_base + r, H - 1) * W + min(x_base + g, W - 1);
-    const float* cp = cur + ((size_t)b * kFastC + 4 * j) * HW + q;
-    cur4[r] = make_float4(__ldg(cp), __ldg(cp + HW), __ldg(cp + 2 * (size_t)HW), __ldg(cp + 3 * (size_t)HW));
+  for (int j = 0; j < kNChunk; ++j) {
+    const float* cp = cur + ((size_t)b * kFastC + 4 * j) * HW + p;
+    cur4[j] = make_float4(__ldg(cp), __ldg(cp + HW), __ldg(cp + 2 * (size_t)HW), __ldg(cp + 3 * (size_t)HW));
   }
   float best = 0.f, best_d = 0.f;
 
   for (int d0 = d_begin; d0 < d_end; d0 += kDC) {
-    float dval[kDC];
+    float dval[kDC], acc[kDC];
 #pragma unroll
     for (int dd = 0; dd < kDC; ++dd) {
       const int d = min(d0 + dd, d_end - 1);
       dval[dd] = PER_PIXEL ? __ldg(planes + ((size_t)b * s.D + d) * HW + p)
                            : __ldg(planes + b * s.D + d);
+      acc[dd] = 0.f;
     }
-    float acc[kDC][4];
-#pragma unroll
-    for (int dd = 0; dd < kDC; ++dd)
-#pragma unroll
-      for (int r = 0; r < 4; ++r) acc[dd][r] = 0.f;
-
 #pragma unroll 1
     for (int k = 0; k < K; ++k) {
       const float* vp = sview + k * kViewFloats;
       float ax, ay, az;
       homography_point(vp, dx, dy, ax, ay, az);
       const float tx = vp[9], ty = vp[10], tz = vp[11];
-      int packed[kDC];
-      float fx[kDC], fy[kDC];
+      const float4* view4 = src4 + (size_t)(b * K + k) * kNChunk * HW;
 #pragma unroll
       for (int dd = 0; dd < kDC; ++dd) {
         float px, py, zp;
@@ -163,51 +176,53 @@ dot_fast_kernel(srcv_shape s, const float* __restrict__ cur, const float4* __res
         Taps tp;
         bilinear_taps(px, py, W, H, ctr, tp);
         const unsigned valid = (zp > 0.0f) ? tp.valid : 0u;  // depth mask folded into the footprint
-        packed[dd] = (tp.y0 * W + tp.x0) * 16 + (int)valid;
-        fx[dd] = tp.fx;
-        fy[dd] = tp.fy;
-      }
-      const float4* view4 = src4 + (size_t)(b * K + k) * HW * 4 + j;
-#pragma unroll
-      for (int dd = 0; dd < kDC; ++dd) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int src_lane = 8 * r + g;
-          const int pk = __shfl_sync(kFull, packed[dd], src_lane);
-          const float hfx = __shfl_sync(kFull, fx[dd], src_lane);
-          const float hfy = __shfl_sync(kFull, fy[dd], src_lane);
-          const float gx = 1.0f - hfx, gy = 1.0f - hfy;
-          const float4* t4 = view4 + (ptrdiff_t)(pk >> 4) * 4;
-          const float4 c4 = cur4[r];
-          float a = acc[dd][r];
-          if (pk & 1) a = fmaf(gx * gy, dot4(__ldg(t4), c4), a);
-          if (pk & 2) a = fmaf(hfx * gy, dot4(__ldg(t4 + 4), c4), a);
-          if (pk & 4) a = fmaf(gx * hfy, dot4(__ldg(t4 + 4 * W), c4), a);
-          if (pk & 8) a = fmaf(hfx * hfy, dot4(__ldg(t4 + 4 * W + 4), c4), a);
-          acc[dd][r] = a;
+        const float gx = 1.0f - tp.fx, gy = 1.0f - tp.fy;
+        const float4* q = view4 + (tp.y0 * W + tp.x0);
+        float t0, t1, t2, t3;
+        if (__all_sync(0xffffffffu, valid == 15u)) {
+          // interior sample for the whole warp: 16 unconditional vector loads
+          t0 = tap_dot<false, HWC>(q, HW, true, cur4);
+          t1 = tap_dot<false, HWC>(q + 1, HW, true, cur4);
+          t2 = tap_dot<false, HWC>(q + W, HW, true, cur4);
+          t3 = tap_dot<false, HWC>(q + W + 1, HW, true, cur4);
+        } else {
+          // border / behind-camera lanes: padding taps are not loaded (zeros)
+          t0 = tap_dot<true, HWC>(q, HW, valid & 1u, cur4);
+          t1 = tap_dot<true, HWC>(q + 1, HW, valid & 2u, cur4);
+          t2 = tap_dot<true, HWC>(q + W, HW, valid & 4u, cur4);
+          t3 = tap_dot<true, HWC>(q + W + 1, HW, valid & 8u, cur4);
         }
+        acc[dd] = fmaf(gx * gy, t0, fmaf(tp.fx * gy, t1, fmaf(gx * tp.fy, t2,
+                       fmaf(tp.fx * tp.fy, t3, acc[dd]))));
       }
     }
-    // reduce the 4 channel chunks of each group, then hand pixel (g, r)'s sum to its owner
 #pragma unroll
     for (int dd = 0; dd < kDC; ++dd) {
-      float mine = 0.f;
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        float a = acc[dd][r];
-        a += __shfl_xor_sync(kFull, a, 1);
-        a += __shfl_xor_sync(kFull, a, 2);
-        const float t = __shfl_sync(kFull, a, 4 * (lane & 7));
-        if ((lane >> 3) == r) mine = t;
-      }
       const int d = d0 + dd;
       if (d < d_end) {
-        if (active) cost[((size_t)b * s.D + d) * HW + p] = mine;
-        argmax_update(mine, dval[dd], best, best_d, d == d_begin);
+        if (active) cost[((size_t)b * s.D + d) * HW + p] = acc[dd];
+        argmax_update(acc[dd], dval[dd], best, best_d, d == d_begin);
       }
     }
   }
   if (fuse_argmax && active) lowest[(size_t)b * HW + p] = best_d;
+}
+
+template <bool PER_PIXEL, int kTileW>
+void launch_fast_sized(const srcv_shape& s, dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                       const float* cur, const float4* src4, const ViewParams* views,
+                       const float* planes, float* cost, float* lowest) {
+#define SRCV_SIZED(TW_, TH_)                                                                   \
+  if (s.W == TW_ && s.H == TH_) {                                                              \
+    dot_fast_kernel<PER_PIXEL, TW_, TH_, kTileW><<<grid, block, smem, stream>>>(s, cur, src4, views,   \
+                                                                        planes, cost, lowest); \
+    return;                                                                                    \
+  }
+  SRCV_SIZED(160, 120)  // 640x480 frames (BASELINE configs)
+  SRCV_SIZED(128, 96)   // 512x384 frames (the reference's default, options.py:70-71)
+  SRCV_SIZED(64, 48)    // 256x192 frames (BASELINE config 0)
+#undef SRCV_SIZED
+  dot_fast_kernel<PER_PIXEL, 0, 0, kTileW><<<grid, block, smem, stream>>>(s, cur, src4, views, planes, cost, lowest);
 }
 
 }  // namespace
@@ -239,18 +254,30 @@ cudaError_t launch_dot_fast(const srcv_shape& s, const float* cur, const Workspa
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static const int tile_w = [] {
+    const char* e = getenv("SRCV_DOT_TILE_W");  // tuning knob: 16 (16x2 warp tile) or 32 (32x1)
+    return (e && atoi(e) == 32) ? 32 : 16;
+  }();
+  const int kTileW = tile_w, kTileH = 32 / tile_w;
   const int tiles_x = (s.W + kTileW - 1) / kTileW;
   const int tiles_y = (s.H + kTileH * kFastWarps - 1) / (kTileH * kFastWarps);
   const long long warps = (long long)s.B * tiles_x * tiles_y * kFastWarps;
+  static const long long want = [] {
+    const char* e = getenv("SRCV_DOT_WARPS_PER_SM");  // tuning knob, default 16
+    return (long long)(e ? atoi(e) : 16);
+  }();
   int d_split = 1;
-  while (d_split < 8 && warps * d_split < 16ll * sms && s.D / (d_split * 2) >= 2 * kDC) d_split *= 2;
+  while (d_split < 8 && warps * d_split < want * sms && s.D / (d_split * 2) >= 2 * kDC) d_split *= 2;
   dim3 grid(tiles_x * tiles_y, s.B, d_split), block(kFastWarps * 32);
   const size_t smem = sizeof(float) * kViewFloats * s.K;
-  const float4* src4 = reinterpret_cast<const float4*>(ws.src_nhwc);
-  if (per_pixel)
-    dot_fast_kernel<true><<<grid, block, smem, stream>>>(s, cur, src4, ws.views, planes, cost, lowest);
-  else
-    dot_fast_kernel<false><<<grid, block, smem, stream>>>(s, cur, src4, ws.views, planes, cost, lowest);
+  const float4* src4 = reinterpret_cast<const float4*>(ws.src_c4);
+  if (tile_w == 32) {
+    if (per_pixel) launch_fast_sized<true, 32>(s, grid, block, smem, stream, cur, src4, ws.views, planes, cost, lowest);
+    else launch_fast_sized<false, 32>(s, grid, block, smem, stream, cur, src4, ws.views, planes, cost, lowest);
+  } else {
+    if (per_pixel) launch_fast_sized<true, 16>(s, grid, block, smem, stream, cur, src4, ws.views, planes, cost, lowest);
+    else launch_fast_sized<false, 16>(s, grid, block, smem, stream, cur, src4, ws.views, planes, cost, lowest);
+  }
   note_launch();
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return err;

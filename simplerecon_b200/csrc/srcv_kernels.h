@@ -14,17 +14,17 @@ struct Workspace {
   float* planes;        // (B,D) plane depths (FROM_RANGE / PER_PLANE copy)
   ViewParams* views;    // (B,K)
   FrameParams* frames;  // (B)
-  float* src_nhwc;      // (B,K,H,W,C) channel-last copy of src_feats, or nullptr
+  float* src_c4;      // (B,K,C/4,H,W,4) chunk-planar copy of src_feats, or nullptr
   float* extra;         // variant-specific scratch, or nullptr
   size_t bytes;         // total bytes needed
 };
 
-Workspace carve_workspace(const srcv_shape& s, void* base, bool want_nhwc, size_t extra_bytes);
+Workspace carve_workspace(const srcv_shape& s, void* base, bool want_c4, size_t extra_bytes);
 
 // counts kernel launches for srcv_launch_count()
 void note_launch(int n = 1);
 
-// prep: view/frame params, plane depths, optional NCHW->NHWC copy of src_feats.
+// prep: view/frame params, plane depths, optional chunk-planar copy of src_feats.
 cudaError_t launch_prep(const srcv_shape& s, const srcv_cameras& cams, const srcv_planes& pl,
                         const float* src_feats, const Workspace& ws, bool need_poses,
                         cudaStream_t stream);
@@ -45,6 +45,15 @@ cudaError_t launch_mlp_generic(const srcv_shape& s, const float* cur, const floa
                                const Workspace& ws, const float* planes, bool per_pixel,
                                const srcv_mlp_weights& w, float* cost, float* lowest,
                                uint8_t* mask, cudaStream_t stream);
+
+// tensor-core variant (tcgen05): K = 7, C = 16, 202 -> 128 -> 128 -> 1
+bool mlp_tc_supported(const srcv_shape& s, const srcv_mlp_weights& w);
+size_t mlp_tc_extra_bytes();
+cudaError_t launch_mlp_tc(const srcv_shape& s, const float* cur, const Workspace& ws,
+                          const float* planes, bool per_pixel, const srcv_mlp_weights& w, float* cost,
+                          float* lowest, uint8_t* mask, cudaStream_t stream);
+cudaError_t launch_tc_selftest(const float* A, const float* Wm, int Kp, float* Dout, void* scratch,
+                               cudaStream_t stream);
 
 // argmax over planes -> plane depth (used by variants that do not fuse it)
 cudaError_t launch_argmax(const srcv_shape& s, const float* cost, const float* planes,

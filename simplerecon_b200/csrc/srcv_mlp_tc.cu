@@ -1,0 +1,544 @@
+// Metadata-MLP plane-sweep volume on the 5th-generation tensor cores (tcgen05).
+//
+// Replaces FeatureVolumeManager / FastFeatureVolumeManager.build_cost_volume
+// (reference modules/cost_volume.py:451-736, :967-1164) for the hero layout
+// K = 7 source views, C = 16 channels, MLP 202 -> 128 -> 128 -> 1.
+//
+// One persistent CTA per SM walks over row tiles; a tile = 128 rows = a 16 x 8 block of
+// pixels at one depth plane.  Per tile
+//   1. eight producer warps (two threads per row: views 0-3 | views 4-6 + the
+//      view-independent channels) project, gather (chunk-planar copy of the source
+//      features, csrc/srcv_prep.cu) and build the row's 202 metadata channels in
+//      registers, split every value into an fp16 (hi, lo) pair and write them straight
+//      into TENSOR MEMORY as the A operand (tcgen05.st) — the (B,F,H,W) / (B*D,H,W,F)
+//      tensors the reference materialises exist only as 208 TMEM columns per row;
+//   2. one thread issues layer 1 as 13 x 3 tcgen05.mma (A from TMEM, weights from
+//      shared memory, fp32 accumulator in TMEM):  A_hi W_hi + A_hi W_lo + A_lo W_hi;
+//   3. four epilogue warps (thread = row) read the accumulator, add bias, LeakyReLU,
+//      split to fp16 (hi, lo) again and write the layer-2 A operand back to TMEM;
+//   4. layer 2 as 8 x 3 tcgen05.mma into the same accumulator columns;
+//   5. the epilogue warps apply bias + LeakyReLU and the 128 -> 1 layer as a dot in
+//      registers and store the cost.
+// The stages are chained by mbarriers (tcgen05.commit for MMA completion), so the
+// producers already build tile t+1 while tile t is in its MMA / epilogue stages.
+// Weights (both layers, hi and lo, 168 KB) stay resident in shared memory for the
+// CTA's lifetime, laid out as K-major no-swizzle core matrices by the pack kernel.
+//
+// The K order of layer 1 is OURS (the pack kernel permutes W1's columns to match):
+//   per view k (26 channels): 16 warped | mask | z' | dot | ray angle | n_src (3) | comb | r | t
+//   tail (20 + 6 pad):        16 reference features | plane depth | n_cur (3) | zeros
+// i.e. every producer thread writes 4 x 26 = 104 consecutive K positions.
+#include "srcv_kernels.h"
+#include "srcv_tc.cuh"
+
+namespace srcv {
+
+namespace {
+
+using namespace tc;
+
+constexpr int kC = 16, kViews = 7;
+constexpr int kRows = 128;               // rows (TMEM lanes) per tile
+constexpr int kTileW = 16, kTileH = 8;   // pixel block of a tile
+constexpr int kN = 128;                  // layer widths
+constexpr int kBlk = kC + 10;            // channels per view block (26)
+constexpr int kK1 = 208;                 // 7*26 + 20 + 6 pad  (13 k-steps of 16)
+constexpr int kK2 = 128;
+constexpr int kF = kC * (kViews + 1) + 10 * kViews + 4;  // 202
+
+// TMEM columns (32-bit): two K elements per column
+constexpr uint32_t kColA1Hi = 0, kColA1Lo = kK1 / 2, kColD = kK1, kColA2Hi = kK1 + kN,
+                   kColA2Lo = kK1 + kN + kK2 / 2, kTmemCols = 512;
+static_assert(kColA2Lo + kK2 / 2 <= kTmemCols, "TMEM budget");
+
+constexpr int kProdWarps = 8, kEpiWarps = 4;
+constexpr int kThreads = (kProdWarps + kEpiWarps + 1) * 32;  // + MMA warp
+constexpr int kMmaWarp = kProdWarps + kEpiWarps;
+
+// shared memory image (bytes)
+constexpr uint32_t kW1Bytes = kN * kK1 * 2, kW2Bytes = kN * kK2 * 2;   // one of (hi, lo)
+constexpr uint32_t kOffW1Hi = 0, kOffW1Lo = kW1Bytes, kOffW2Hi = 2 * kW1Bytes,
+                   kOffW2Lo = 2 * kW1Bytes + kW2Bytes, kOffVec = 2 * kW1Bytes + 2 * kW2Bytes;
+constexpr uint32_t kVecFloats = 3 * kN + 4;   // b1 | b2 | w3 | b3
+constexpr uint32_t kOffBar = kOffVec + kVecFloats * 4;
+constexpr uint32_t kOffFlag = kOffBar + 8 * 8;            // 8 mbarrier slots
+constexpr uint32_t kSmemBytes = kOffFlag + 2 * 2 * kRows; // mask bits [parity][half][row]
+// image = [W1hi | W1lo | W2hi | W2lo | b1 b2 w3 b3] exactly as it sits in shared memory
+constexpr uint32_t kImageBytes = kOffBar;
+
+// K-major no-swizzle core-matrix offset (in halves) of element (n, k) of an N x Kp operand
+__host__ __device__ inline uint32_t core_offset(int n, int k, int N) {
+  return (uint32_t)(k >> 3) * (uint32_t)(N * 8) + (uint32_t)(n >> 3) * 64u + (uint32_t)(n & 7) * 8u + (uint32_t)(k & 7);
+}
+
+// reference channel index (modules/cost_volume.py:698-723 order) of OUR layer-1 K position
+__host__ __device__ inline int ref_channel(int kk) {
+  if (kk < kViews * kBlk) {
+    const int k = kk / kBlk, j = kk - k * kBlk;
+    if (j < kC) return k * kC + j;                       // warped features
+    const int base = kC * (kViews + 1);                  // 128
+    switch (j - kC) {
+      case 0: return base + k;                           // mask
+      case 1: return base + kViews + k;                  // z'
+      case 2: return base + 2 * kViews + 1 + k;          // dot
+      case 3: return base + 3 * kViews + 1 + k;          // ray angle
+      case 4: case 5: case 6: return base + 4 * kViews + 4 + 3 * k + (j - kC - 4);  // n_src
+      case 7: return base + 7 * kViews + 4 + k;          // comb
+      case 8: return base + 8 * kViews + 4 + k;          // r
+      default: return base + 9 * kViews + 4 + k;         // t
+    }
+  }
+  const int j = kk - kViews * kBlk;
+  if (j < kC) return kViews * kC + j;                    // reference-frame features
+  if (j == kC) return kC * (kViews + 1) + 2 * kViews;    // plane depth
+  if (j < kC + 4) return kC * (kViews + 1) + 4 * kViews + 1 + (j - kC - 1);  // n_cur
+  return -1;                                             // pad
+}
+
+// Builds the shared-memory image from nn.Linear weights: fp16 (hi, lo) core matrices.
+__global__ void __launch_bounds__(256)
+tc_pack_kernel(srcv_mlp_weights w, uint8_t* __restrict__ image) {
+  __half* w1hi = reinterpret_cast<__half*>(image + kOffW1Hi);
+  __half* w1lo = reinterpret_cast<__half*>(image + kOffW1Lo);
+  __half* w2hi = reinterpret_cast<__half*>(image + kOffW2Hi);
+  __half* w2lo = reinterpret_cast<__half*>(image + kOffW2Lo);
+  float* vec = reinterpret_cast<float*>(image + kOffVec);
+  const int n1 = kN * kK1, n2 = kN * kK2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2 + (int)kVecFloats;
+       i += gridDim.x * blockDim.x) {
+    if (i < n1) {
+      const int n = i / kK1, kk = i - n * kK1;
+      const int f = ref_channel(kk);
+      const float v = f >= 0 ? w.w1[(size_t)n * kF + f] : 0.f;
+      const __half h = __float2half_rn(v);
+      w1hi[core_offset(n, kk, kN)] = h;
+      w1lo[core_offset(n, kk, kN)] = __float2half_rn(v - __half2float(h));
+    } else if (i < n1 + n2) {
+      const int q = i - n1, n = q / kK2, kk = q - n * kK2;
+      const float v = w.w2[(size_t)n * kK2 + kk];
+      const __half h = __float2half_rn(v);
+      w2hi[core_offset(n, kk, kN)] = h;
+      w2lo[core_offset(n, kk, kN)] = __float2half_rn(v - __half2float(h));
+    } else {
+      const int q = i - n1 - n2;
+      float v = 0.f;
+      if (q < kN) v = w.b1[q];
+      else if (q < 2 * kN) v = w.b2[q - kN];
+      else if (q < 3 * kN) v = w.w3[q - 2 * kN];
+      else if (q == 3 * kN) v = w.b3[0];
+      vec[q] = v;
+    }
+  }
+}
+
+// 13 packed columns (26 values) of one K block -> TMEM (hi and lo regions)
+__device__ __forceinline__ void store_block(uint32_t tbase_lane, uint32_t col, const float (&v)[kBlk]) {
+  uint32_t hi[13], lo[13];
+#pragma unroll
+  for (int i = 0; i < 13; ++i) split_pack(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+  st_x8(tbase_lane + kColA1Hi + col, hi);
+  st_x4(tbase_lane + kColA1Hi + col + 8, hi + 8);
+  st_x1(tbase_lane + kColA1Hi + col + 12, hi[12]);
+  st_x8(tbase_lane + kColA1Lo + col, lo);
+  st_x4(tbase_lane + kColA1Lo + col + 8, lo + 8);
+  st_x1(tbase_lane + kColA1Lo + col + 12, lo[12]);
+}
+
+// issue D (+)= A_hi W_hi + A_hi W_lo + A_lo W_hi over `ksteps` K steps of 16
+__device__ __forceinline__ void issue_layer(uint32_t tmem_base, uint32_t col_hi, uint32_t col_lo,
+                                            uint32_t smem_hi, uint32_t smem_lo, int ksteps) {
+  constexpr uint32_t idesc = idesc_f16_f32(kRows, kN);
+  constexpr uint32_t kLbo = kN * 16, kSbo = 128, kStepBytes = 2 * kLbo;  // two 8-wide K chunks per MMA
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const uint64_t bhi = smem_desc(smem_hi + ks * kStepBytes, kLbo, kSbo);
+    const uint64_t blo = smem_desc(smem_lo + ks * kStepBytes, kLbo, kSbo);
+    const uint32_t ahi = tmem_base + col_hi + ks * 8, alo = tmem_base + col_lo + ks * 8;
+    mma_ts(tmem_base + kColD, ahi, bhi, idesc, ks > 0 ? 1u : 0u);
+    mma_ts(tmem_base + kColD, ahi, blo, idesc, 1u);
+    mma_ts(tmem_base + kColD, alo, bhi, idesc, 1u);
+  }
+}
+
+struct TileCoord { int b, d, x0, y0; };
+
+__device__ __forceinline__ TileCoord tile_coord(long long id, int D, int tiles_x, int tiles_xy) {
+  TileCoord t;
+  t.d = (int)(id % D);
+  const long long r = id / D;
+  const int txy = (int)(r % tiles_xy);
+  t.b = (int)(r / tiles_xy);
+  t.x0 = (txy % tiles_x) * kTileW;
+  t.y0 = (txy / tiles_x) * kTileH;
+  return t;
+}
+
+template <bool PER_PIXEL>
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_tc_kernel(srcv_shape s, const float* __restrict__ cur, const float4* __restrict__ src4,
+              const ViewParams* __restrict__ views, const FrameParams* __restrict__ frames,
+              const float* __restrict__ planes, const uint8_t* __restrict__ image,
+              float* __restrict__ cost, uint8_t* __restrict__ mask_out, long long num_tiles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t s_tmem_base;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* bar_a1_full = bars + 0;   // producers -> MMA   (256 arrivals)
+  uint64_t* bar_mma1 = bars + 1;      // layer-1 MMAs done  (commit)
+  uint64_t* bar_a2_full = bars + 2;   // epilogue -> MMA    (128 arrivals)
+  uint64_t* bar_mma2 = bars + 3;      // layer-2 MMAs done  (commit)
+  uint64_t* bar_d_free = bars + 4;    // epilogue done reading the accumulator (128 arrivals)
+  uint8_t* sflag = smem + kOffFlag;
+  const float* svec = reinterpret_cast<const float*>(smem + kOffVec);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int W = s.W, H = s.H, HW = W * H, D = s.D;
+  const int tiles_x = (W + kTileW - 1) / kTileW, tiles_xy = tiles_x * ((H + kTileH - 1) / kTileH);
+
+  // ---- one-time setup ----------------------------------------------------------------
+  {
+    const uint4* g = reinterpret_cast<const uint4*>(image);
+    uint4* sdst = reinterpret_cast<uint4*>(smem);
+    for (uint32_t i = tid; i < kImageBytes / 16; i += kThreads) sdst[i] = __ldg(g + i);
+  }
+  if (tid == 0) {
+    mbar_init(bar_a1_full, kProdWarps * 32);
+    mbar_init(bar_mma1, 1);
+    mbar_init(bar_a2_full, kEpiWarps * 32);
+    mbar_init(bar_mma2, 1);
+    mbar_init(bar_d_free, kEpiWarps * 32);
+    mbar_fence_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc(&s_tmem_base, kTmemCols);
+  fence_proxy_async_smem();   // weight image: generic-proxy stores -> tensor-core reads
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = s_tmem_base;
+  const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+
+  if (warp < kProdWarps) {
+    // =============================== producers =========================================
+    const int row = tid & (kRows - 1), half = tid >> 7;   // half 0: views 0-3, half 1: views 4-6 + tail
+    const int rx = row & (kTileW - 1), ry = row >> 4;
+    const Centre ctr(W, H);
+    int it = 0;
+    for (long long id = blockIdx.x; id < num_tiles; id += gridDim.x, ++it) {
+      const TileCoord t = tile_coord(id, D, tiles_x, tiles_xy);
+      const int ox = min(t.x0 + rx, W - 1), oy = min(t.y0 + ry, H - 1);
+      const int p = oy * W + ox;
+      const float pxc = (float)ox + 0.5f, pyc = (float)oy + 0.5f;
+      const float dval = PER_PIXEL ? __ldg(planes + ((size_t)t.b * D + t.d) * HW + p)
+                                   : __ldg(planes + t.b * D + t.d);
+      float4 cur4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float* cp = cur + ((size_t)t.b * kC + 4 * j) * HW + p;
+        cur4[j] = make_float4(__ldg(cp), __ldg(cp + HW), __ldg(cp + 2 * (size_t)HW), __ldg(cp + 3 * (size_t)HW));
+      }
+      // rays: X = d * (invK3 p); n_cur = X / |X|
+      const FrameParams& fp = frames[t.b];
+      const float rxv = fmaf(fp.invK[0], pxc, fmaf(fp.invK[1], pyc, fp.invK[2]));
+      const float ryv = fmaf(fp.invK[3], pxc, fmaf(fp.invK[4], pyc, fp.invK[5]));
+      const float rzv = fmaf(fp.invK[6], pxc, fmaf(fp.invK[7], pyc, fp.invK[8]));
+      const float X = dval * rxv, Y = dval * ryv, Z = dval * rzv;
+      const float nc = fmaxf(sqrtf(fmaf(X, X, fmaf(Y, Y, Z * Z))), kEpsNorm);
+      const float cx = X / nc, cy = Y / nc, cz = Z / nc;
+      const float n1 = fmaxf(sqrtf(fmaf(cx, cx, fmaf(cy, cy, cz * cz))), kEpsCos);
+      const float cxn = cx / n1, cyn = cy / n1, czn = cz / n1;
+
+      // A1 is free once the previous tile's layer-1 MMAs have completed
+      mbar_wait(bar_mma1, (it & 1) ^ 1);
+      fence_after_sync();
+
+      unsigned bits = 0;
+      const int k_begin = half ? 4 : 0, k_end = half ? kViews : 4;
+      for (int k = k_begin; k < k_end; ++k) {
+        const ViewParams& vp = views[t.b * kViews + k];
+        float ax, ay, az, px, py, zp;
+        homography_point(vp.a0, pxc - ctr.half_w, pyc - ctr.half_h, ax, ay, az);
+        project_point(dval, ax, ay, az, vp.t[0], vp.t[1], vp.t[2], px, py, zp);
+        Taps tp;
+        bilinear_taps(px, py, W, H, ctr, tp);
+        const float gx = 1.0f - tp.fx, gy = 1.0f - tp.fy;
+        const float wgt[4] = {gx * gy, tp.fx * gy, gx * tp.fy, tp.fx * tp.fy};
+        const int off[4] = {0, 1, W, W + 1};
+        const float4* q = src4 + (size_t)(t.b * kViews + k) * 4 * HW + (tp.y0 * W + tp.x0);
+        float v[kBlk];
+#pragma unroll
+        for (int c = 0; c < kC; ++c) v[c] = 0.f;
+        // features are sampled even for points behind the camera (only the dot is masked,
+        // reference modules/cost_volume.py:590-623); padding taps contribute zeros
+#pragma unroll
+        for (int tap = 0; tap < 4; ++tap) {
+          if ((tp.valid >> tap) & 1u) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 f = __ldg(q + off[tap] + (size_t)j * HW);
+              v[4 * j + 0] = fmaf(wgt[tap], f.x, v[4 * j + 0]);
+              v[4 * j + 1] = fmaf(wgt[tap], f.y, v[4 * j + 1]);
+              v[4 * j + 2] = fmaf(wgt[tap], f.z, v[4 * j + 2]);
+              v[4 * j + 3] = fmaf(wgt[tap], f.w, v[4 * j + 3]);
+            }
+          }
+        }
+        float dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          dot = fmaf(v[4 * j], cur4[j].x, fmaf(v[4 * j + 1], cur4[j].y,
+                fmaf(v[4 * j + 2], cur4[j].z, fmaf(v[4 * j + 3], cur4[j].w, dot))));
+        const float mk = zp > 0.0f ? 1.0f : 0.0f;
+        // n_src = (X - centre_k)/|.| ; ray angle = cosine_similarity(n_cur, n_src, eps 1e-5)
+        const float sx0 = X - vp.centre[0], sy0 = Y - vp.centre[1], sz0 = Z - vp.centre[2];
+        const float ns = fmaxf(sqrtf(fmaf(sx0, sx0, fmaf(sy0, sy0, sz0 * sz0))), kEpsNorm);
+        const float sx = sx0 / ns, sy = sy0 / ns, sz = sz0 / ns;
+        const float n2 = fmaxf(sqrtf(fmaf(sx, sx, fmaf(sy, sy, sz * sz))), kEpsCos);
+        v[kC + 0] = mk;
+        v[kC + 1] = zp;
+        v[kC + 2] = dot * mk;
+        v[kC + 3] = fmaf(cxn, sx / n2, fmaf(cyn, sy / n2, czn * (sz / n2)));
+        v[kC + 4] = sx; v[kC + 5] = sy; v[kC + 6] = sz;
+        v[kC + 7] = vp.comb; v[kC + 8] = vp.rmeas; v[kC + 9] = vp.tmeas;
+        store_block(lane_base, (uint32_t)(13 * k), v);
+        if (zp > 0.0f) bits |= 1u;
+        if (in_mask_bounds(px, py, W, H, ctr)) bits |= 2u;
+      }
+      if (half) {
+        float v[kBlk];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[4 * j] = cur4[j].x; v[4 * j + 1] = cur4[j].y; v[4 * j + 2] = cur4[j].z; v[4 * j + 3] = cur4[j].w;
+        }
+        v[kC] = dval; v[kC + 1] = cx; v[kC + 2] = cy; v[kC + 3] = cz;
+#pragma unroll
+        for (int j = kC + 4; j < kBlk; ++j) v[j] = 0.f;
+        store_block(lane_base, (uint32_t)(13 * kViews), v);
+      }
+      sflag[((it & 1) * 2 + half) * kRows + row] = (uint8_t)bits;
+      wait_st();
+      fence_before_sync();
+      mbar_arrive(bar_a1_full);
+    }
+  } else if (warp < kMmaWarp) {
+    // =============================== epilogue ===========================================
+    const int row = tid - kProdWarps * 32;
+    const int rx = row & (kTileW - 1), ry = row >> 4;
+    int it = 0;
+    for (long long id = blockIdx.x; id < num_tiles; id += gridDim.x, ++it) {
+      const TileCoord t = tile_coord(id, D, tiles_x, tiles_xy);
+      const int ox = t.x0 + rx, oy = t.y0 + ry;
+      const bool active = ox < W && oy < H;
+      // ---- layer-1 epilogue: bias + LeakyReLU, (hi, lo) split, A2 -> TMEM --------------
+      mbar_wait(bar_mma1, it & 1);
+      fence_after_sync();
+#pragma unroll 1
+      for (int c0 = 0; c0 < kN; c0 += 32) {
+        uint32_t r[32];
+        ld_x32(lane_base + kColD + c0, r);
+        wait_ld();
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float a = leaky(__uint_as_float(r[2 * j]) + svec[c0 + 2 * j]);
+          const float b = leaky(__uint_as_float(r[2 * j + 1]) + svec[c0 + 2 * j + 1]);
+          split_pack(a, b, hi[j], lo[j]);
+        }
+        st_x16(lane_base + kColA2Hi + c0 / 2, hi);
+        st_x16(lane_base + kColA2Lo + c0 / 2, lo);
+      }
+      wait_st();
+      fence_before_sync();
+      mbar_arrive(bar_a2_full);
+      // ---- layer-2 epilogue: bias + LeakyReLU, 128 -> 1 dot, store -----------------------
+      mbar_wait(bar_mma2, it & 1);
+      fence_after_sync();
+      float acc = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < kN; c0 += 32) {
+        uint32_t r[32];
+        ld_x32(lane_base + kColD + c0, r);
+        wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          acc = fmaf(leaky(__uint_as_float(r[j]) + svec[kN + c0 + j]), svec[2 * kN + c0 + j], acc);
+      }
+      fence_before_sync();
+      mbar_arrive(bar_d_free);
+      if (active) {
+        const int p = oy * W + ox;
+        cost[((size_t)t.b * D + t.d) * HW + p] = acc + svec[3 * kN];
+        if (mask_out != nullptr && t.d == D - 1) {
+          const unsigned bits = sflag[((it & 1) * 2 + 0) * kRows + row] | sflag[((it & 1) * 2 + 1) * kRows + row];
+          mask_out[(size_t)t.b * HW + p] = (bits == 3u) ? 1 : 0;
+        }
+      }
+    }
+  } else {
+    // =============================== MMA issuer ==========================================
+    const uint32_t sbase = smem_u32(smem);
+    int it = 0;
+    for (long long id = blockIdx.x; id < num_tiles; id += gridDim.x, ++it) {
+      mbar_wait(bar_a1_full, it & 1);          // A1 of this tile is in TMEM
+      mbar_wait(bar_d_free, (it & 1) ^ 1);     // previous tile's accumulator has been read
+      fence_after_sync();
+      if (lane == 0) {
+        issue_layer(tmem_base, kColA1Hi, kColA1Lo, sbase + kOffW1Hi, sbase + kOffW1Lo, kK1 / 16);
+        mma_commit(bar_mma1);
+      }
+      __syncwarp();
+      mbar_wait(bar_a2_full, it & 1);          // A2 written, accumulator columns consumed
+      fence_after_sync();
+      if (lane == 0) {
+        issue_layer(tmem_base, kColA2Hi, kColA2Lo, sbase + kOffW2Hi, sbase + kOffW2Lo, kK2 / 16);
+        mma_commit(bar_mma2);
+      }
+      __syncwarp();
+    }
+  }
+  // ---- teardown ---------------------------------------------------------------------------
+  fence_before_sync();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// self-test: D[128,128] = A[128,Kp] W[128,Kp]^T through the same TMEM / descriptor / barrier
+// machinery (A split and written to TMEM by the row threads, W packed to core matrices).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tc_selftest_pack(const float* __restrict__ Wm, int Kp, __half* __restrict__ hi, __half* __restrict__ lo) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kN * Kp; i += gridDim.x * blockDim.x) {
+    const int n = i / Kp, k = i - n * Kp;
+    const float v = Wm[i];
+    const __half h = __float2half_rn(v);
+    hi[core_offset(n, k, kN)] = h;
+    lo[core_offset(n, k, kN)] = __float2half_rn(v - __half2float(h));
+  }
+}
+
+__global__ void __launch_bounds__(160, 1)
+tc_selftest_kernel(const float* __restrict__ A, const __half* __restrict__ whi,
+                   const __half* __restrict__ wlo, int Kp, float* __restrict__ Dout) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t s_tmem_base;
+  __shared__ uint64_t bar_a, bar_d;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t wbytes = (uint32_t)kN * Kp * 2;
+  for (uint32_t i = tid; i < wbytes / 16; i += blockDim.x) {
+    reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(whi) + i);
+    reinterpret_cast<uint4*>(smem + wbytes)[i] = __ldg(reinterpret_cast<const uint4*>(wlo) + i);
+  }
+  if (tid == 0) { mbar_init(&bar_a, 128); mbar_init(&bar_d, 1); mbar_fence_init(); }
+  if (warp == 4) tmem_alloc(&s_tmem_base, kTmemCols);
+  fence_proxy_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = s_tmem_base;
+  const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint32_t col_lo = Kp / 2, col_d = 256;
+  if (warp < 4) {
+    const float* a = A + (size_t)tid * Kp;
+    for (int c = 0; c < Kp / 2; c += 8) {
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split_pack(a[2 * (c + j)], a[2 * (c + j) + 1], hi[j], lo[j]);
+      st_x8(lane_base + c, hi);
+      st_x8(lane_base + col_lo + c, lo);
+    }
+    wait_st();
+    fence_before_sync();
+    mbar_arrive(&bar_a);
+    mbar_wait(&bar_d, 0);
+    fence_after_sync();
+    for (int c0 = 0; c0 < kN; c0 += 32) {
+      uint32_t r[32];
+      ld_x32(lane_base + col_d + c0, r);
+      wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) Dout[(size_t)tid * kN + c0 + j] = __uint_as_float(r[j]);
+    }
+  } else {
+    mbar_wait(&bar_a, 0);
+    fence_after_sync();
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_f16_f32(kRows, kN);
+      constexpr uint32_t kLbo = kN * 16, kSbo = 128;
+      const uint32_t sb = smem_u32(smem);
+      for (int ks = 0; ks < Kp / 16; ++ks) {
+        const uint64_t bhi = smem_desc(sb + ks * 2 * kLbo, kLbo, kSbo);
+        const uint64_t blo = smem_desc(sb + wbytes + ks * 2 * kLbo, kLbo, kSbo);
+        mma_ts(tmem_base + col_d, tmem_base + ks * 8, bhi, idesc, ks > 0 ? 1u : 0u);
+        mma_ts(tmem_base + col_d, tmem_base + ks * 8, blo, idesc, 1u);
+        mma_ts(tmem_base + col_d, tmem_base + col_lo + ks * 8, bhi, idesc, 1u);
+      }
+      mma_commit(&bar_d);
+    }
+    __syncwarp();
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 4) { fence_after_sync(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+}  // namespace
+
+bool mlp_tc_supported(const srcv_shape& s, const srcv_mlp_weights& w) {
+  return s.K == kViews && s.C == kC && w.hidden1 == kN && w.hidden2 == kN &&
+         (long long)s.H * s.W < (1ll << 26);
+}
+
+size_t mlp_tc_extra_bytes() { return (kImageBytes + 255) & ~(size_t)255; }
+
+cudaError_t launch_mlp_tc(const srcv_shape& s, const float* cur, const Workspace& ws,
+                          const float* planes, bool per_pixel, const srcv_mlp_weights& w, float* cost,
+                          float* lowest, uint8_t* mask, cudaStream_t stream) {
+  uint8_t* image = reinterpret_cast<uint8_t*>(ws.extra);
+  tc_pack_kernel<<<64, 256, 0, stream>>>(w, image);
+  note_launch();
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return err;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles_x = (s.W + kTileW - 1) / kTileW, tiles_y = (s.H + kTileH - 1) / kTileH;
+  const long long num_tiles = (long long)s.B * s.D * tiles_x * tiles_y;
+  const int grid = (int)(num_tiles < sms ? num_tiles : sms);
+  const float4* src4 = reinterpret_cast<const float4*>(ws.src_c4);
+  if (per_pixel) {
+    err = cudaFuncSetAttribute(mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (err != cudaSuccess) return err;
+    mlp_tc_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(s, cur, src4, ws.views, ws.frames, planes,
+                                                               image, cost, mask, num_tiles);
+  } else {
+    err = cudaFuncSetAttribute(mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (err != cudaSuccess) return err;
+    mlp_tc_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(s, cur, src4, ws.views, ws.frames, planes,
+                                                                image, cost, mask, num_tiles);
+  }
+  note_launch();
+  err = cudaGetLastError();
+  if (err != cudaSuccess) return err;
+  if (lowest) err = launch_argmax(s, cost, planes, per_pixel, lowest, stream);
+  return err;
+}
+
+// D (128 x 128) = A (128 x Kp) W^T (128 x Kp), Kp a multiple of 16 and <= 256; `scratch`
+// needs 2 * 128 * Kp halves.  Device pointers; test hook for tests/test_gpu_tc.py.
+cudaError_t launch_tc_selftest(const float* A, const float* Wm, int Kp, float* Dout, void* scratch,
+                               cudaStream_t stream) {
+  if (Kp % 16 != 0 || Kp <= 0 || Kp > 256) return cudaErrorInvalidValue;
+  __half* hi = reinterpret_cast<__half*>(scratch);
+  __half* lo = hi + (size_t)kN * Kp;
+  tc_selftest_pack<<<32, 256, 0, stream>>>(Wm, Kp, hi, lo);
+  note_launch();
+  const size_t smem = (size_t)2 * kN * Kp * 2;
+  cudaError_t err = cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  tc_selftest_kernel<<<1, 160, smem, stream>>>(A, hi, lo, Kp, Dout);
+  note_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace srcv

@@ -6,9 +6,9 @@
 //  * per frame: invK[:3,:3] for the rays (utils/geometry_utils.py:56);
 //  * plane depths  d_i = exp(log(min) + log(max/min) ramp_i)
 //    (reference modules/cost_volume.py:124-127) when the caller gives a range;
-//  * optionally the channel-last (B,K,H,W,C) copy of the source features that the
-//    fast kernels gather from: one 64-byte texel per (view, pixel) so a bilinear
-//    tap is four 16-byte vector loads instead of C scalar ones.
+//  * optionally the chunk-planar (B,K,C/4,H,W,4) copy of the source features that
+//    the fast kernels gather from: a bilinear tap is C/4 16-byte vector loads and
+//    horizontally adjacent pixels read adjacent vectors.
 #include "srcv_kernels.h"
 
 namespace srcv {
@@ -74,32 +74,26 @@ __device__ void view_params(const float* __restrict__ Kmat, const float* __restr
 __global__ void __launch_bounds__(256)
 prep_kernel(srcv_shape s, srcv_cameras cams, srcv_planes pl, const float* __restrict__ src,
             float* __restrict__ planes_ws, ViewParams* __restrict__ views,
-            FrameParams* __restrict__ frames, float* __restrict__ src_nhwc) {
+            FrameParams* __restrict__ frames, float* __restrict__ src_c4) {
   const long long nv = (long long)s.B * s.K;
   const long long nf = s.B;
   const long long np = (pl.mode == SRCV_PLANES_FROM_RANGE) ? (long long)s.B * s.D : 0;
   const long long HW = (long long)s.H * s.W;
-  const long long nt = src_nhwc ? nv * HW : 0;
+  const long long nt = src_c4 ? nv * (s.C / 4) * HW : 0;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nt) {
-    // NCHW -> NHWC: thread = one texel.  Reads are coalesced across the warp
-    // (consecutive pixels of one channel plane); each thread writes its C floats
-    // contiguously.
-    const long long bk = i / HW, p = i - bk * HW;
-    const float* in = src + bk * s.C * HW + p;
-    float* out = src_nhwc + i * s.C;
-    if ((s.C & 3) == 0) {
-      for (int c = 0; c < s.C; c += 4) {
-        float4 v;
-        v.x = __ldg(in + (c + 0) * HW);
-        v.y = __ldg(in + (c + 1) * HW);
-        v.z = __ldg(in + (c + 2) * HW);
-        v.w = __ldg(in + (c + 3) * HW);
-        *reinterpret_cast<float4*>(out + c) = v;
-      }
-    } else {
-      for (int c = 0; c < s.C; ++c) out[c] = __ldg(in + c * HW);
-    }
+    // NCHW -> chunk-planar (B,K,C/4,H,W,4): thread = one (view, chunk, pixel).  Reads
+    // (4 channel planes) and the float4 write are both coalesced across the warp.
+    const long long nch = s.C / 4;
+    const long long bkj = i / HW, p = i - bkj * HW;      // bkj = (b*K + k)*nch + j
+    const float* in = src + bkj * 4 * HW + p;            // channel 4j of view (b,k)
+    float4 v;
+    v.x = __ldg(in);
+    v.y = __ldg(in + HW);
+    v.z = __ldg(in + 2 * HW);
+    v.w = __ldg(in + 3 * HW);
+    reinterpret_cast<float4*>(src_c4)[i] = v;
+    (void)nch;
     return;
   }
   i -= nt;
@@ -152,7 +146,7 @@ argmax_kernel(srcv_shape s, const float* __restrict__ cost, const float* __restr
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-Workspace carve_workspace(const srcv_shape& s, void* base, bool want_nhwc, size_t extra_bytes) {
+Workspace carve_workspace(const srcv_shape& s, void* base, bool want_c4, size_t extra_bytes) {
   Workspace ws{};
   size_t off = 0;
   char* p = static_cast<char*>(base);
@@ -164,13 +158,13 @@ Workspace carve_workspace(const srcv_shape& s, void* base, bool want_nhwc, size_
   ws.planes = reinterpret_cast<float*>(take(sizeof(float) * (size_t)s.B * s.D));
   ws.views = reinterpret_cast<ViewParams*>(take(sizeof(ViewParams) * (size_t)s.B * s.K));
   ws.frames = reinterpret_cast<FrameParams*>(take(sizeof(FrameParams) * (size_t)s.B));
-  if (want_nhwc) {
-    ws.src_nhwc = reinterpret_cast<float*>(
+  if (want_c4) {
+    ws.src_c4 = reinterpret_cast<float*>(
         take(sizeof(float) * (size_t)s.B * s.K * s.C * s.H * s.W));
   }
   if (extra_bytes) ws.extra = reinterpret_cast<float*>(take(extra_bytes));
   ws.bytes = off;
-  if (!p) { ws.planes = nullptr; ws.views = nullptr; ws.frames = nullptr; ws.src_nhwc = nullptr; ws.extra = nullptr; }
+  if (!p) { ws.planes = nullptr; ws.views = nullptr; ws.frames = nullptr; ws.src_c4 = nullptr; ws.extra = nullptr; }
   return ws;
 }
 
@@ -181,12 +175,12 @@ cudaError_t launch_prep(const srcv_shape& s, const srcv_cameras& cams, const src
   if (!need_poses) c.src_poses = nullptr;
   const long long nv = (long long)s.B * s.K;
   const long long np = (pl.mode == SRCV_PLANES_FROM_RANGE) ? (long long)s.B * s.D : 0;
-  const long long nt = ws.src_nhwc ? nv * s.H * s.W : 0;
+  const long long nt = ws.src_c4 ? nv * (s.C / 4) * s.H * s.W : 0;
   const long long total = nt + nv + s.B + np;
   const int threads = 256;
   const long long blocks = (total + threads - 1) / threads;
   prep_kernel<<<(unsigned)blocks, threads, 0, stream>>>(s, c, pl, src_feats, ws.planes, ws.views,
-                                                        ws.frames, ws.src_nhwc);
+                                                        ws.frames, ws.src_c4);
   note_launch();
   return cudaGetLastError();
 }

@@ -46,7 +46,9 @@ def run_gpu(kind, inputs, D, sd=None, variant="auto", return_mask=True, fast_cls
 
 def fast_ok(kind, inputs):
     B, K, C, H, W = inputs["src_feats"].shape
-    return kind == "dot" and C == 16 and K <= 8
+    if kind == "dot":
+        return C == 16                      # chunk-planar gather kernel
+    return C == 16 and K == 7               # tcgen05 kernel: hero layout (hidden widths 128/128)
 
 
 # --------------------------------------------------------------------------- #
@@ -60,7 +62,7 @@ def test_golden(name, variant):
     if variant == "fast" and not fast_ok(kind, inputs):
         pytest.skip("fast variant does not cover this shape")
     (cost, lowest, planes, mask), used = run_gpu(kind, inputs, g["D"], sd, variant)
-    assert ("fast" in used) == (variant == "fast"), used
+    assert (("fast" in used) or ("tc" in used)) == (variant == "fast"), used
     assert cost.is_contiguous() and cost.dtype == torch.float32 and cost.is_cuda
     assert_cost_close(kind, cost, g["ref_cost"], g["ref_cost64"], what=f"{name}/{variant}")
     ref_planes = g["ref_planes"]
@@ -96,21 +98,26 @@ def test_dot_vs_oracle(B, K, H, W, D, seed, smooth, variant):
     assert mask is None
 
 
+@pytest.mark.parametrize("variant", ["generic", "fast"])
 @pytest.mark.parametrize("B,K,C,H,W,D,seed", [
     (1, 7, 16, 30, 40, 16, 5),
+    (2, 7, 16, 37, 53, 3, 15),         # partial 16x8 tiles on both borders
     (2, 3, 16, 21, 19, 5, 6),
     (1, 2, 8, 16, 24, 4, 7),           # C != 16
 ])
-def test_mlp_vs_oracle(B, K, C, H, W, D, seed):
+def test_mlp_vs_oracle(B, K, C, H, W, D, seed, variant):
     t = make_tuple(B, K, H, W, channels=C, seed=seed)
+    if variant == "fast" and not fast_ok("mlp", t):
+        pytest.skip("tensor-core variant covers the hero layout only")
     sd = mlp_state(K, C, seed=seed)
-    (cost, lowest, planes, mask), used = run_gpu("mlp", t, D, sd)
+    (cost, lowest, planes, mask), used = run_gpu("mlp", t, D, sd, variant)
+    assert ("tc" in used) == (variant == "fast"), used
     w = O.mlp_weights_from_state_dict(sd)
     oc, ol, op, om = O.forward_mlp(**t, weights=w, num_depth_bins=D, return_mask=True)
     assert_cost_close("mlp", cost, oc, what=f"mlp {used}")
     assert_mask_close(mask, om)
     # without return_mask the mask is None, like the reference
-    (c2, _, _, m2), _ = run_gpu("mlp", t, D, sd, return_mask=False)
+    (c2, _, _, m2), _ = run_gpu("mlp", t, D, sd, variant, return_mask=False)
     assert m2 is None and torch.equal(c2, cost)
 
 
@@ -163,6 +170,7 @@ def test_full_size_hero_cfg2_two_frames():
     t = make_workload_tuple(w, batch=2)
     sd = mlp_state(7, 16, seed=0)
     (cost, lowest, planes, mask), used = run_gpu("mlp", t, w.planes, sd)
+    assert "tc" in used, used
     assert cost.shape == (2, 64, 120, 160) and mask.shape == (2, 120, 160) and mask.dtype == torch.bool
     t0 = {k: (v[:1] if v.dim() > 0 and v.shape[0] == 2 else v) for k, v in t.items()}
     wts = O.mlp_weights_from_state_dict(sd)
@@ -179,6 +187,10 @@ def test_full_size_hero_cfg2_two_frames():
     assert torch.equal(torch.gather(planes.expand_as(cost), 1, idx).squeeze(1), lowest)
     (cost_f, _, _, mask_f), _ = run_gpu("mlp", t, w.planes, sd, fast_cls=True)
     assert torch.equal(cost_f, cost) and torch.equal(mask_f, mask)
+    # the fp32 SIMT variant agrees with the tensor-core variant
+    (cost_g, _, _, mask_g), used_g = run_gpu("mlp", t, w.planes, sd, variant="generic")
+    assert "generic" in used_g and torch.equal(mask_g, mask)
+    assert (cost_g - cost).abs().max().item() <= cost_tol("mlp", oc)
 
 
 # --------------------------------------------------------------------------- #
