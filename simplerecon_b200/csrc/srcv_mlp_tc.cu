@@ -51,6 +51,10 @@ constexpr uint32_t kColA1Hi = 0, kColA1Lo = kK1 / 2, kColD = kK1, kColA2Hi = kK1
                    kColA2Lo = kK1 + kN + kK2 / 2, kTmemCols = 512;
 static_assert(kColA2Lo + kK2 / 2 <= kTmemCols, "TMEM budget");
 
+// Weights are stored x16 (exact) so that the lo halves of typical |w| ~ 0.05 weights stay
+// out of the fp16 subnormal range; the epilogues fold the 1/16 into their bias FMA.
+constexpr float kWScale = 16.0f, kWUnscale = 1.0f / 16.0f;
+
 constexpr int kProdWarps = 8, kEpiWarps = 4;
 constexpr int kThreads = (kProdWarps + kEpiWarps + 1) * 32;  // + MMA warp
 constexpr int kMmaWarp = kProdWarps + kEpiWarps;
@@ -109,13 +113,13 @@ tc_pack_kernel(srcv_mlp_weights w, uint8_t* __restrict__ image) {
     if (i < n1) {
       const int n = i / kK1, kk = i - n * kK1;
       const int f = ref_channel(kk);
-      const float v = f >= 0 ? w.w1[(size_t)n * kF + f] : 0.f;
+      const float v = kWScale * (f >= 0 ? w.w1[(size_t)n * kF + f] : 0.f);
       const __half h = __float2half_rn(v);
       w1hi[core_offset(n, kk, kN)] = h;
       w1lo[core_offset(n, kk, kN)] = __float2half_rn(v - __half2float(h));
     } else if (i < n1 + n2) {
       const int q = i - n1, n = q / kK2, kk = q - n * kK2;
-      const float v = w.w2[(size_t)n * kK2 + kk];
+      const float v = kWScale * w.w2[(size_t)n * kK2 + kk];
       const __half h = __float2half_rn(v);
       w2hi[core_offset(n, kk, kN)] = h;
       w2lo[core_offset(n, kk, kN)] = __float2half_rn(v - __half2float(h));
@@ -337,8 +341,8 @@ mlp_tc_kernel(srcv_shape s, const float* __restrict__ cur, const float4* __restr
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float a = leaky(__uint_as_float(r[2 * j]) + svec[c0 + 2 * j]);
-          const float b = leaky(__uint_as_float(r[2 * j + 1]) + svec[c0 + 2 * j + 1]);
+          const float a = leaky(fmaf(__uint_as_float(r[2 * j]), kWUnscale, svec[c0 + 2 * j]));
+          const float b = leaky(fmaf(__uint_as_float(r[2 * j + 1]), kWUnscale, svec[c0 + 2 * j + 1]));
           split_pack(a, b, hi[j], lo[j]);
         }
         st_x16(lane_base + kColA2Hi + c0 / 2, hi);
@@ -358,7 +362,7 @@ mlp_tc_kernel(srcv_shape s, const float* __restrict__ cur, const float4* __restr
         wait_ld();
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          acc = fmaf(leaky(__uint_as_float(r[j]) + svec[kN + c0 + j]), svec[2 * kN + c0 + j], acc);
+          acc = fmaf(leaky(fmaf(__uint_as_float(r[j]), kWUnscale, svec[kN + c0 + j])), svec[2 * kN + c0 + j], acc);
       }
       fence_before_sync();
       mbar_arrive(bar_d_free);

@@ -28,7 +28,8 @@ def test_tc_gemm_matches_fp64(cuda_device, built_lib, Kp, scale):
     # fp32 product noise: |A||W| sqrt(K) 2^-22-ish; fp32 matmul itself is no better
     ref32 = (A @ Wm.t()).double()
     e32 = (ref32 - ref).abs().max().item()
-    bound = 4 * max(e32, 1e-7 * float(ref.abs().max()))
+    # ... plus the fp16-subnormal floor of the lo halves (|x| < ~0.1 keeps an absolute 3e-8)
+    bound = 4 * max(e32, 1e-7 * float(ref.abs().max())) + 6e-8 * 0.07 * Kp ** 0.5 * 2
     assert err <= bound, f"tcgen05 GEMM err {err:.3e} (fp32 matmul err {e32:.3e})"
 
 
