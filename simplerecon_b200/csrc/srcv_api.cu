@@ -152,11 +152,12 @@ int32_t srcv_dot_forward_f32(const srcv_shape* s, const float* cur, const float*
   const Workspace need = carve_workspace(*s, nullptr, dot_fast_supported(*s), 0);
   if (int32_t e = check_workspace(workspace, workspace_bytes, need.bytes)) return e;
   Workspace ws = carve_workspace(*s, workspace, dot_fast_supported(*s), 0);
-  if (!fast) ws.src_c4 = nullptr;  // skip the chunk-planar copy
+  if (!fast) ws.src_c4 = nullptr;  // skip the chunk-planar copies
+  ws.cur_c4 = nullptr;             // the dot kernel keeps the reference features in registers
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ProfRecord* pr = prof_next();
   if (pr) cudaEventRecord(pr->e[0], stream);
-  cudaError_t err = launch_prep(*s, *cams, *pl, src, ws, false, stream);
+  cudaError_t err = launch_prep(*s, *cams, *pl, src, cur, ws, false, stream);
   if (err != cudaSuccess) return cuda_fail(err, "prep");
   if (pr) cudaEventRecord(pr->e[1], stream);
   const bool per_pixel = pl->mode == SRCV_PLANES_PER_PIXEL;
@@ -219,7 +220,7 @@ int32_t srcv_mlp_forward_f32(const srcv_shape* s, const float* cur, const float*
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ProfRecord* pr = prof_next();
   if (pr) cudaEventRecord(pr->e[0], stream);
-  cudaError_t err = launch_prep(*s, *cams, *pl, src, ws, true, stream);
+  cudaError_t err = launch_prep(*s, *cams, *pl, src, cur, ws, true, stream);
   if (err != cudaSuccess) return cuda_fail(err, "prep");
   if (pr) cudaEventRecord(pr->e[1], stream);
   const bool per_pixel = pl->mode == SRCV_PLANES_PER_PIXEL;

@@ -121,7 +121,16 @@ __device__ __forceinline__ bool in_mask_bounds(float px, float py, int W, int H,
   return px > 2.0f - ox && px < (float)(W - 2) - ox && py > 2.0f - oy && py < (float)(H - 2) - oy;
 }
 
-__device__ __forceinline__ float leaky(float x) { return x > 0.0f ? x : kLeaky * x; }
+__device__ __forceinline__ float leaky(float x) { return fmaxf(x, kLeaky * x); }
+
+// 1 / max(sqrt(s), eps) for s >= 0: hardware rsqrt + one Newton step (< 1 ulp), no
+// division and no IEEE-sqrt slow path.  Used for F.normalize / cosine_similarity.
+__device__ __forceinline__ float inv_norm(float s, float eps) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(s));
+  y = y * fmaf(-0.5f * s, y * y, 1.5f);
+  return (s > eps * eps) ? y : __frcp_rn(eps);
+}
 
 // argmax update with torch.argmax semantics: first index wins ties, NaN is max.
 __device__ __forceinline__ void argmax_update(float v, float dval, float& best, float& best_d,

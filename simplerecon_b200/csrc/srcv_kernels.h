@@ -14,7 +14,8 @@ struct Workspace {
   float* planes;        // (B,D) plane depths (FROM_RANGE / PER_PLANE copy)
   ViewParams* views;    // (B,K)
   FrameParams* frames;  // (B)
-  float* src_c4;      // (B,K,C/4,H,W,4) chunk-planar copy of src_feats, or nullptr
+  float* src_c4;        // (B,K,C/4,H,W,4) chunk-planar copy of src_feats, or nullptr
+  float* cur_c4;        // (B,C/4,H,W,4) chunk-planar copy of cur_feats, or nullptr
   float* extra;         // variant-specific scratch, or nullptr
   size_t bytes;         // total bytes needed
 };
@@ -26,8 +27,8 @@ void note_launch(int n = 1);
 
 // prep: view/frame params, plane depths, optional chunk-planar copy of src_feats.
 cudaError_t launch_prep(const srcv_shape& s, const srcv_cameras& cams, const srcv_planes& pl,
-                        const float* src_feats, const Workspace& ws, bool need_poses,
-                        cudaStream_t stream);
+                        const float* src_feats, const float* cur_feats, const Workspace& ws,
+                        bool need_poses, cudaStream_t stream);
 
 // dot-product volume
 cudaError_t launch_dot_generic(const srcv_shape& s, const float* cur, const float* src,

@@ -6,8 +6,8 @@
 //
 // One persistent CTA per SM walks over row tiles; a tile = 128 rows = a 16 x 8 block of
 // pixels at one depth plane.  Per tile
-//   1. eight producer warps (two threads per row: views 0-3 | views 4-6 + the
-//      view-independent channels) project, gather (chunk-planar copy of the source
+//   1. sixteen producer warps (four threads per row: views {0,1} | {2,3} | {4,5} | {6 + the
+//      view-independent channels}) project, gather (chunk-planar copy of the source
 //      features, csrc/srcv_prep.cu) and build the row's 202 metadata channels in
 //      registers, split every value into an fp16 (hi, lo) pair and write them straight
 //      into TENSOR MEMORY as the A operand (tcgen05.st) — the (B,F,H,W) / (B*D,H,W,F)
@@ -27,7 +27,9 @@
 // The K order of layer 1 is OURS (the pack kernel permutes W1's columns to match):
 //   per view k (26 channels): 16 warped | mask | z' | dot | ray angle | n_src (3) | comb | r | t
 //   tail (20 + 6 pad):        16 reference features | plane depth | n_cur (3) | zeros
-// i.e. every producer thread writes 4 x 26 = 104 consecutive K positions.
+// i.e. every producer thread writes 2 x 26 = 52 consecutive K positions; the first of its
+// two blocks is computed before it waits for the A columns to be free, so producing tile
+// t+1 overlaps the layer-1 MMAs of tile t.
 #include "srcv_kernels.h"
 #include "srcv_tc.cuh"
 
@@ -55,9 +57,18 @@ static_assert(kColA2Lo + kK2 / 2 <= kTmemCols, "TMEM budget");
 // out of the fp16 subnormal range; the epilogues fold the 1/16 into their bias FMA.
 constexpr float kWScale = 16.0f, kWUnscale = 1.0f / 16.0f;
 
-constexpr int kProdWarps = 8, kEpiWarps = 4;
-constexpr int kThreads = (kProdWarps + kEpiWarps + 1) * 32;  // + MMA warp
+constexpr int kProdWarps = 16, kEpiWarps = 4;   // 4 producer threads per row
 constexpr int kMmaWarp = kProdWarps + kEpiWarps;
+// Register allocation is per 4-warp group, so the CTA is launched as 24 warps x 80
+// registers (61440 of the SM's 65536): warps 0-15 producers, 16-19 epilogue, 20 the MMA
+// issuer, 21-23 idle fillers of its warpgroup.  setmaxnreg then re-balances WITHIN that
+// launch allocation (it cannot draw on the SM's unallocated registers): the epilogue group
+// drops to 56, the MMA group to 40, and the four producer groups grow to 96.
+constexpr int kThreads = (kProdWarps + kEpiWarps + 4) * 32;
+constexpr int kRegsLaunch = 80, kRegsProd = 96, kRegsEpi = 56, kRegsMma = 40;
+static_assert(kThreads * kRegsLaunch <= 65536, "launch allocation");
+static_assert(kProdWarps * 32 * kRegsProd + kEpiWarps * 32 * kRegsEpi + 128 * kRegsMma <= kThreads * kRegsLaunch,
+              "setmaxnreg budget must fit the CTA's launch allocation");
 
 // shared memory image (bytes)
 constexpr uint32_t kW1Bytes = kN * kK1 * 2, kW2Bytes = kN * kK2 * 2;   // one of (hi, lo)
@@ -66,7 +77,7 @@ constexpr uint32_t kOffW1Hi = 0, kOffW1Lo = kW1Bytes, kOffW2Hi = 2 * kW1Bytes,
 constexpr uint32_t kVecFloats = 3 * kN + 4;   // b1 | b2 | w3 | b3
 constexpr uint32_t kOffBar = kOffVec + kVecFloats * 4;
 constexpr uint32_t kOffFlag = kOffBar + 8 * 8;            // 8 mbarrier slots
-constexpr uint32_t kSmemBytes = kOffFlag + 2 * 2 * kRows; // mask bits [parity][half][row]
+constexpr uint32_t kSmemBytes = kOffFlag + 2 * 4 * kRows; // mask bits [parity][quarter][row]
 // image = [W1hi | W1lo | W2hi | W2lo | b1 b2 w3 b3] exactly as it sits in shared memory
 constexpr uint32_t kImageBytes = kOffBar;
 
@@ -135,11 +146,14 @@ tc_pack_kernel(srcv_mlp_weights w, uint8_t* __restrict__ image) {
   }
 }
 
-// 13 packed columns (26 values) of one K block -> TMEM (hi and lo regions)
-__device__ __forceinline__ void store_block(uint32_t tbase_lane, uint32_t col, const float (&v)[kBlk]) {
-  uint32_t hi[13], lo[13];
+// 26 values of one K block -> 13 packed (hi, lo) column pairs
+__device__ __forceinline__ void split_block(const float (&v)[kBlk], uint32_t (&hi)[13], uint32_t (&lo)[13]) {
 #pragma unroll
   for (int i = 0; i < 13; ++i) split_pack(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+}
+// 13 packed columns of one K block -> TMEM (hi and lo regions)
+__device__ __forceinline__ void store_block(uint32_t tbase_lane, uint32_t col, const uint32_t (&hi)[13],
+                                            const uint32_t (&lo)[13]) {
   st_x8(tbase_lane + kColA1Hi + col, hi);
   st_x4(tbase_lane + kColA1Hi + col + 8, hi + 8);
   st_x1(tbase_lane + kColA1Hi + col + 12, hi[12]);
@@ -148,18 +162,104 @@ __device__ __forceinline__ void store_block(uint32_t tbase_lane, uint32_t col, c
   st_x1(tbase_lane + kColA1Lo + col + 12, lo[12]);
 }
 
-// issue D (+)= A_hi W_hi + A_hi W_lo + A_lo W_hi over `ksteps` K steps of 16
+// Per-row quantities shared by the view blocks of one tile.
+struct RowCtx {
+  float dval, dxc, dyc;      // plane depth, centred pixel
+  float X, Y, Z;             // back-projected point
+  float cxn, cyn, czn;       // n_cur / max(|n_cur|, eps_cos)  (cosine_similarity operand)
+  float4 cur4[4];            // reference-frame features of the pixel
+};
+
+// One source view of one row: project, gather, metadata (channel order of the K block).
+// HWC != 0: compile-time map size, every gather address is base + immediate.
+template <int TW, int HWC>
+__device__ __forceinline__ unsigned view_block(const RowCtx& rc, const ViewParams& vp,
+                                               const float4* __restrict__ view4, int Wrt, int H, int HWrt,
+                                               const Centre& ctr, float (&v)[kBlk]) {
+  const int W = TW ? TW : Wrt, HW = HWC ? HWC : HWrt;
+  float ax, ay, az, px, py, zp;
+  homography_point(vp.a0, rc.dxc, rc.dyc, ax, ay, az);
+  project_point(rc.dval, ax, ay, az, vp.t[0], vp.t[1], vp.t[2], px, py, zp);
+  Taps tp;
+  bilinear_taps(px, py, W, H, ctr, tp);
+  const float gx = 1.0f - tp.fx, gy = 1.0f - tp.fy;
+  const float wgt[4] = {gx * gy, tp.fx * gy, gx * tp.fy, tp.fx * tp.fy};
+  const int off[4] = {0, 1, W, W + 1};
+  const float4* q = view4 + (tp.y0 * W + tp.x0);
+  // features are sampled even for points behind the camera (only the dot is masked,
+  // reference modules/cost_volume.py:590-623); padding taps contribute zeros
+  // two taps (8 vector loads) in flight at a time keeps the producer inside its register budget
+  const bool interior = __all_sync(0xffffffffu, tp.valid == 15u);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    float4 f[2][4];
+#pragma unroll
+    for (int tt = 0; tt < 2; ++tt) {
+      const int tap = 2 * half + tt;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (interior) f[tt][j] = __ldg(q + off[tap] + (size_t)j * HW);
+        else f[tt][j] = ((tp.valid >> tap) & 1u) ? __ldg(q + off[tap] + (size_t)j * HW)
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    const float wa = wgt[2 * half], wb = wgt[2 * half + 1];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (half == 0) {
+        v[4 * j + 0] = fmaf(wa, f[0][j].x, wb * f[1][j].x);
+        v[4 * j + 1] = fmaf(wa, f[0][j].y, wb * f[1][j].y);
+        v[4 * j + 2] = fmaf(wa, f[0][j].z, wb * f[1][j].z);
+        v[4 * j + 3] = fmaf(wa, f[0][j].w, wb * f[1][j].w);
+      } else {
+        v[4 * j + 0] = fmaf(wa, f[0][j].x, fmaf(wb, f[1][j].x, v[4 * j + 0]));
+        v[4 * j + 1] = fmaf(wa, f[0][j].y, fmaf(wb, f[1][j].y, v[4 * j + 1]));
+        v[4 * j + 2] = fmaf(wa, f[0][j].z, fmaf(wb, f[1][j].z, v[4 * j + 2]));
+        v[4 * j + 3] = fmaf(wa, f[0][j].w, fmaf(wb, f[1][j].w, v[4 * j + 3]));
+      }
+    }
+  }
+  float dot = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    dot = fmaf(v[4 * j], rc.cur4[j].x, fmaf(v[4 * j + 1], rc.cur4[j].y,
+          fmaf(v[4 * j + 2], rc.cur4[j].z, fmaf(v[4 * j + 3], rc.cur4[j].w, dot))));
+  const float mk = zp > 0.0f ? 1.0f : 0.0f;
+  // n_src = (X - centre_k)/max(|.|, 1e-12) ; ray angle = cosine_similarity(n_cur, n_src, eps 1e-5)
+  const float sx0 = rc.X - vp.centre[0], sy0 = rc.Y - vp.centre[1], sz0 = rc.Z - vp.centre[2];
+  const float is = inv_norm(fmaf(sx0, sx0, fmaf(sy0, sy0, sz0 * sz0)), kEpsNorm);
+  const float sx = sx0 * is, sy = sy0 * is, sz = sz0 * is;
+  const float i2 = inv_norm(fmaf(sx, sx, fmaf(sy, sy, sz * sz)), kEpsCos);
+  v[kC + 0] = mk;
+  v[kC + 1] = zp;
+  v[kC + 2] = dot * mk;
+  v[kC + 3] = fmaf(rc.cxn, sx * i2, fmaf(rc.cyn, sy * i2, rc.czn * (sz * i2)));
+  v[kC + 4] = sx; v[kC + 5] = sy; v[kC + 6] = sz;
+  v[kC + 7] = vp.comb; v[kC + 8] = vp.rmeas; v[kC + 9] = vp.tmeas;
+  unsigned bits = 0;
+  if (zp > 0.0f) bits |= 1u;
+  if (in_mask_bounds(px, py, W, H, ctr)) bits |= 2u;
+  return bits;
+}
+
+// issue D (+)= A_hi W_hi + A_hi W_lo + A_lo W_hi over KSTEPS K steps of 16
+template <int KSTEPS>
 __device__ __forceinline__ void issue_layer(uint32_t tmem_base, uint32_t col_hi, uint32_t col_lo,
-                                            uint32_t smem_hi, uint32_t smem_lo, int ksteps) {
+                                            uint32_t smem_hi, uint32_t smem_lo) {
   constexpr uint32_t idesc = idesc_f16_f32(kRows, kN);
   constexpr uint32_t kLbo = kN * 16, kSbo = 128, kStepBytes = 2 * kLbo;  // two 8-wide K chunks per MMA
-  for (int ks = 0; ks < ksteps; ++ks) {
-    const uint64_t bhi = smem_desc(smem_hi + ks * kStepBytes, kLbo, kSbo);
-    const uint64_t blo = smem_desc(smem_lo + ks * kStepBytes, kLbo, kSbo);
-    const uint32_t ahi = tmem_base + col_hi + ks * 8, alo = tmem_base + col_lo + ks * 8;
-    mma_ts(tmem_base + kColD, ahi, bhi, idesc, ks > 0 ? 1u : 0u);
-    mma_ts(tmem_base + kColD, ahi, blo, idesc, 1u);
-    mma_ts(tmem_base + kColD, alo, bhi, idesc, 1u);
+  // only the 14-bit start-address field changes from step to step
+  const uint64_t bhi0 = smem_desc(smem_hi, kLbo, kSbo), blo0 = smem_desc(smem_lo, kLbo, kSbo);
+  const uint32_t d = tmem_base + kColD;
+  uint64_t bhi = bhi0, blo = blo0;
+  uint32_t ahi = tmem_base + col_hi, alo = tmem_base + col_lo;
+#pragma unroll 1
+  for (int ks = 0; ks < KSTEPS; ++ks) {
+    mma_ts(d, ahi, bhi, idesc, ks > 0 ? 1u : 0u);
+    mma_ts(d, ahi, blo, idesc, 1u);
+    mma_ts(d, alo, bhi, idesc, 1u);
+    bhi += kStepBytes >> 4; blo += kStepBytes >> 4;
+    ahi += 8; alo += 8;
   }
 }
 
@@ -176,9 +276,9 @@ __device__ __forceinline__ TileCoord tile_coord(long long id, int D, int tiles_x
   return t;
 }
 
-template <bool PER_PIXEL>
+template <bool PER_PIXEL, int TW, int TH>
 __global__ void __launch_bounds__(kThreads, 1)
-mlp_tc_kernel(srcv_shape s, const float* __restrict__ cur, const float4* __restrict__ src4,
+mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __restrict__ src4,
               const ViewParams* __restrict__ views, const FrameParams* __restrict__ frames,
               const float* __restrict__ planes, const uint8_t* __restrict__ image,
               float* __restrict__ cost, uint8_t* __restrict__ mask_out, long long num_tiles) {
@@ -194,7 +294,8 @@ mlp_tc_kernel(srcv_shape s, const float* __restrict__ cur, const float4* __restr
   const float* svec = reinterpret_cast<const float*>(smem + kOffVec);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int W = s.W, H = s.H, HW = W * H, D = s.D;
+  const int W = TW ? TW : s.W, H = TH ? TH : s.H, HW = W * H, D = s.D;
+  constexpr int HWC = TW * TH;
   const int tiles_x = (W + kTileW - 1) / kTileW, tiles_xy = tiles_x * ((H + kTileH - 1) / kTileH);
 
   // ---- one-time setup ----------------------------------------------------------------
@@ -220,8 +321,10 @@ mlp_tc_kernel(srcv_shape s, const float* __restrict__ cur, const float4* __restr
   const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
 
   if (warp < kProdWarps) {
+    reg_inc<kRegsProd>();
     // =============================== producers =========================================
-    const int row = tid & (kRows - 1), half = tid >> 7;   // half 0: views 0-3, half 1: views 4-6 + tail
+    // four threads per row: quarter q builds views {2q, 2q+1}; q = 3 builds view 6 + the tail
+    const int row = tid & (kRows - 1), quarter = tid >> 7;
     const int rx = row & (kTileW - 1), ry = row >> 4;
     const Centre ctr(W, H);
     int it = 0;
@@ -230,98 +333,61 @@ mlp_tc_kernel(srcv_shape s, const float* __restrict__ cur, const float4* __restr
       const int ox = min(t.x0 + rx, W - 1), oy = min(t.y0 + ry, H - 1);
       const int p = oy * W + ox;
       const float pxc = (float)ox + 0.5f, pyc = (float)oy + 0.5f;
-      const float dval = PER_PIXEL ? __ldg(planes + ((size_t)t.b * D + t.d) * HW + p)
-                                   : __ldg(planes + t.b * D + t.d);
-      float4 cur4[4];
+      RowCtx rc;
+      rc.dval = PER_PIXEL ? __ldg(planes + ((size_t)t.b * D + t.d) * HW + p)
+                          : __ldg(planes + t.b * D + t.d);
+      rc.dxc = pxc - ctr.half_w;
+      rc.dyc = pyc - ctr.half_h;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float* cp = cur + ((size_t)t.b * kC + 4 * j) * HW + p;
-        cur4[j] = make_float4(__ldg(cp), __ldg(cp + HW), __ldg(cp + 2 * (size_t)HW), __ldg(cp + 3 * (size_t)HW));
-      }
+      for (int j = 0; j < 4; ++j) rc.cur4[j] = __ldg(cur4g + ((size_t)t.b * 4 + j) * HW + p);
       // rays: X = d * (invK3 p); n_cur = X / |X|
       const FrameParams& fp = frames[t.b];
       const float rxv = fmaf(fp.invK[0], pxc, fmaf(fp.invK[1], pyc, fp.invK[2]));
       const float ryv = fmaf(fp.invK[3], pxc, fmaf(fp.invK[4], pyc, fp.invK[5]));
       const float rzv = fmaf(fp.invK[6], pxc, fmaf(fp.invK[7], pyc, fp.invK[8]));
-      const float X = dval * rxv, Y = dval * ryv, Z = dval * rzv;
-      const float nc = fmaxf(sqrtf(fmaf(X, X, fmaf(Y, Y, Z * Z))), kEpsNorm);
-      const float cx = X / nc, cy = Y / nc, cz = Z / nc;
-      const float n1 = fmaxf(sqrtf(fmaf(cx, cx, fmaf(cy, cy, cz * cz))), kEpsCos);
-      const float cxn = cx / n1, cyn = cy / n1, czn = cz / n1;
+      rc.X = rc.dval * rxv; rc.Y = rc.dval * ryv; rc.Z = rc.dval * rzv;
+      const float ic = inv_norm(fmaf(rc.X, rc.X, fmaf(rc.Y, rc.Y, rc.Z * rc.Z)), kEpsNorm);
+      const float cx = rc.X * ic, cy = rc.Y * ic, cz = rc.Z * ic;
+      const float i1 = inv_norm(fmaf(cx, cx, fmaf(cy, cy, cz * cz)), kEpsCos);
+      rc.cxn = cx * i1; rc.cyn = cy * i1; rc.czn = cz * i1;
 
+      const int k0 = 2 * quarter;
+      const float4* view_base = src4 + (size_t)(t.b * kViews) * 4 * HW;
+      uint32_t hi[13], lo[13];
+      unsigned bits;
+      {
+        // first block is built BEFORE the wait: it overlaps the previous tile's layer-1 MMAs
+        float v[kBlk];
+        bits = view_block<TW, HWC>(rc, views[t.b * kViews + k0], view_base + (size_t)k0 * 4 * HW, W, H, HW, ctr, v);
+        split_block(v, hi, lo);
+      }
       // A1 is free once the previous tile's layer-1 MMAs have completed
       mbar_wait(bar_mma1, (it & 1) ^ 1);
       fence_after_sync();
-
-      unsigned bits = 0;
-      const int k_begin = half ? 4 : 0, k_end = half ? kViews : 4;
-      for (int k = k_begin; k < k_end; ++k) {
-        const ViewParams& vp = views[t.b * kViews + k];
-        float ax, ay, az, px, py, zp;
-        homography_point(vp.a0, pxc - ctr.half_w, pyc - ctr.half_h, ax, ay, az);
-        project_point(dval, ax, ay, az, vp.t[0], vp.t[1], vp.t[2], px, py, zp);
-        Taps tp;
-        bilinear_taps(px, py, W, H, ctr, tp);
-        const float gx = 1.0f - tp.fx, gy = 1.0f - tp.fy;
-        const float wgt[4] = {gx * gy, tp.fx * gy, gx * tp.fy, tp.fx * tp.fy};
-        const int off[4] = {0, 1, W, W + 1};
-        const float4* q = src4 + (size_t)(t.b * kViews + k) * 4 * HW + (tp.y0 * W + tp.x0);
+      store_block(lane_base, (uint32_t)(13 * k0), hi, lo);
+      {
         float v[kBlk];
+        if (quarter < 3) {
+          bits |= view_block<TW, HWC>(rc, views[t.b * kViews + k0 + 1], view_base + (size_t)(k0 + 1) * 4 * HW, W, H, HW, ctr, v);
+        } else {
 #pragma unroll
-        for (int c = 0; c < kC; ++c) v[c] = 0.f;
-        // features are sampled even for points behind the camera (only the dot is masked,
-        // reference modules/cost_volume.py:590-623); padding taps contribute zeros
-#pragma unroll
-        for (int tap = 0; tap < 4; ++tap) {
-          if ((tp.valid >> tap) & 1u) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 f = __ldg(q + off[tap] + (size_t)j * HW);
-              v[4 * j + 0] = fmaf(wgt[tap], f.x, v[4 * j + 0]);
-              v[4 * j + 1] = fmaf(wgt[tap], f.y, v[4 * j + 1]);
-              v[4 * j + 2] = fmaf(wgt[tap], f.z, v[4 * j + 2]);
-              v[4 * j + 3] = fmaf(wgt[tap], f.w, v[4 * j + 3]);
-            }
+          for (int j = 0; j < 4; ++j) {
+            v[4 * j] = rc.cur4[j].x; v[4 * j + 1] = rc.cur4[j].y; v[4 * j + 2] = rc.cur4[j].z; v[4 * j + 3] = rc.cur4[j].w;
           }
+          v[kC] = rc.dval; v[kC + 1] = cx; v[kC + 2] = cy; v[kC + 3] = cz;
+#pragma unroll
+          for (int j = kC + 4; j < kBlk; ++j) v[j] = 0.f;
         }
-        float dot = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          dot = fmaf(v[4 * j], cur4[j].x, fmaf(v[4 * j + 1], cur4[j].y,
-                fmaf(v[4 * j + 2], cur4[j].z, fmaf(v[4 * j + 3], cur4[j].w, dot))));
-        const float mk = zp > 0.0f ? 1.0f : 0.0f;
-        // n_src = (X - centre_k)/|.| ; ray angle = cosine_similarity(n_cur, n_src, eps 1e-5)
-        const float sx0 = X - vp.centre[0], sy0 = Y - vp.centre[1], sz0 = Z - vp.centre[2];
-        const float ns = fmaxf(sqrtf(fmaf(sx0, sx0, fmaf(sy0, sy0, sz0 * sz0))), kEpsNorm);
-        const float sx = sx0 / ns, sy = sy0 / ns, sz = sz0 / ns;
-        const float n2 = fmaxf(sqrtf(fmaf(sx, sx, fmaf(sy, sy, sz * sz))), kEpsCos);
-        v[kC + 0] = mk;
-        v[kC + 1] = zp;
-        v[kC + 2] = dot * mk;
-        v[kC + 3] = fmaf(cxn, sx / n2, fmaf(cyn, sy / n2, czn * (sz / n2)));
-        v[kC + 4] = sx; v[kC + 5] = sy; v[kC + 6] = sz;
-        v[kC + 7] = vp.comb; v[kC + 8] = vp.rmeas; v[kC + 9] = vp.tmeas;
-        store_block(lane_base, (uint32_t)(13 * k), v);
-        if (zp > 0.0f) bits |= 1u;
-        if (in_mask_bounds(px, py, W, H, ctr)) bits |= 2u;
+        split_block(v, hi, lo);
       }
-      if (half) {
-        float v[kBlk];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          v[4 * j] = cur4[j].x; v[4 * j + 1] = cur4[j].y; v[4 * j + 2] = cur4[j].z; v[4 * j + 3] = cur4[j].w;
-        }
-        v[kC] = dval; v[kC + 1] = cx; v[kC + 2] = cy; v[kC + 3] = cz;
-#pragma unroll
-        for (int j = kC + 4; j < kBlk; ++j) v[j] = 0.f;
-        store_block(lane_base, (uint32_t)(13 * kViews), v);
-      }
-      sflag[((it & 1) * 2 + half) * kRows + row] = (uint8_t)bits;
+      store_block(lane_base, (uint32_t)(13 * (k0 + 1)), hi, lo);
+      sflag[((it & 1) * 4 + quarter) * kRows + row] = (uint8_t)bits;
       wait_st();
       fence_before_sync();
       mbar_arrive(bar_a1_full);
     }
   } else if (warp < kMmaWarp) {
+    reg_dec<kRegsEpi>();
     // =============================== epilogue ===========================================
     const int row = tid - kProdWarps * 32;
     const int rx = row & (kTileW - 1), ry = row >> 4;
@@ -334,19 +400,20 @@ mlp_tc_kernel(srcv_shape s, const float* __restrict__ cur, const float4* __restr
       mbar_wait(bar_mma1, it & 1);
       fence_after_sync();
 #pragma unroll 1
-      for (int c0 = 0; c0 < kN; c0 += 32) {
-        uint32_t r[32];
-        ld_x32(lane_base + kColD + c0, r);
+      for (int c0 = 0; c0 < kN; c0 += 16) {
+        uint32_t r[16];
+        ld_x16(lane_base + kColD + c0, r);
         wait_ld();
-        uint32_t hi[16], lo[16];
+        uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float a = leaky(fmaf(__uint_as_float(r[2 * j]), kWUnscale, svec[c0 + 2 * j]));
-          const float b = leaky(fmaf(__uint_as_float(r[2 * j + 1]), kWUnscale, svec[c0 + 2 * j + 1]));
+        for (int j = 0; j < 8; ++j) {
+          const float2 bb = *reinterpret_cast<const float2*>(svec + c0 + 2 * j);
+          const float a = leaky(fmaf(__uint_as_float(r[2 * j]), kWUnscale, bb.x));
+          const float b = leaky(fmaf(__uint_as_float(r[2 * j + 1]), kWUnscale, bb.y));
           split_pack(a, b, hi[j], lo[j]);
         }
-        st_x16(lane_base + kColA2Hi + c0 / 2, hi);
-        st_x16(lane_base + kColA2Lo + c0 / 2, lo);
+        st_x8(lane_base + kColA2Hi + c0 / 2, hi);
+        st_x8(lane_base + kColA2Lo + c0 / 2, lo);
       }
       wait_st();
       fence_before_sync();
@@ -356,13 +423,19 @@ mlp_tc_kernel(srcv_shape s, const float* __restrict__ cur, const float4* __restr
       fence_after_sync();
       float acc = 0.f;
 #pragma unroll 1
-      for (int c0 = 0; c0 < kN; c0 += 32) {
-        uint32_t r[32];
-        ld_x32(lane_base + kColD + c0, r);
+      for (int c0 = 0; c0 < kN; c0 += 16) {
+        uint32_t r[16];
+        ld_x16(lane_base + kColD + c0, r);
         wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          acc = fmaf(leaky(fmaf(__uint_as_float(r[j]), kWUnscale, svec[kN + c0 + j])), svec[2 * kN + c0 + j], acc);
+        for (int j = 0; j < 16; j += 4) {
+          const float4 bb = *reinterpret_cast<const float4*>(svec + kN + c0 + j);
+          const float4 ww = *reinterpret_cast<const float4*>(svec + 2 * kN + c0 + j);
+          acc = fmaf(leaky(fmaf(__uint_as_float(r[j + 0]), kWUnscale, bb.x)), ww.x, acc);
+          acc = fmaf(leaky(fmaf(__uint_as_float(r[j + 1]), kWUnscale, bb.y)), ww.y, acc);
+          acc = fmaf(leaky(fmaf(__uint_as_float(r[j + 2]), kWUnscale, bb.z)), ww.z, acc);
+          acc = fmaf(leaky(fmaf(__uint_as_float(r[j + 3]), kWUnscale, bb.w)), ww.w, acc);
+        }
       }
       fence_before_sync();
       mbar_arrive(bar_d_free);
@@ -370,28 +443,30 @@ mlp_tc_kernel(srcv_shape s, const float* __restrict__ cur, const float4* __restr
         const int p = oy * W + ox;
         cost[((size_t)t.b * D + t.d) * HW + p] = acc + svec[3 * kN];
         if (mask_out != nullptr && t.d == D - 1) {
-          const unsigned bits = sflag[((it & 1) * 2 + 0) * kRows + row] | sflag[((it & 1) * 2 + 1) * kRows + row];
+          const uint8_t* fl = sflag + (it & 1) * 4 * kRows + row;
+          const unsigned bits = fl[0] | fl[kRows] | fl[2 * kRows] | fl[3 * kRows];
           mask_out[(size_t)t.b * HW + p] = (bits == 3u) ? 1 : 0;
         }
       }
     }
   } else {
+    reg_dec<kRegsMma>();
     // =============================== MMA issuer ==========================================
     const uint32_t sbase = smem_u32(smem);
     int it = 0;
-    for (long long id = blockIdx.x; id < num_tiles; id += gridDim.x, ++it) {
+    for (long long id = blockIdx.x; warp == kMmaWarp && id < num_tiles; id += gridDim.x, ++it) {
       mbar_wait(bar_a1_full, it & 1);          // A1 of this tile is in TMEM
       mbar_wait(bar_d_free, (it & 1) ^ 1);     // previous tile's accumulator has been read
       fence_after_sync();
       if (lane == 0) {
-        issue_layer(tmem_base, kColA1Hi, kColA1Lo, sbase + kOffW1Hi, sbase + kOffW1Lo, kK1 / 16);
+        issue_layer<kK1 / 16>(tmem_base, kColA1Hi, kColA1Lo, sbase + kOffW1Hi, sbase + kOffW1Lo);
         mma_commit(bar_mma1);
       }
       __syncwarp();
       mbar_wait(bar_a2_full, it & 1);          // A2 written, accumulator columns consumed
       fence_after_sync();
       if (lane == 0) {
-        issue_layer(tmem_base, kColA2Hi, kColA2Lo, sbase + kOffW2Hi, sbase + kOffW2Lo, kK2 / 16);
+        issue_layer<kK2 / 16>(tmem_base, kColA2Hi, kColA2Lo, sbase + kOffW2Hi, sbase + kOffW2Lo);
         mma_commit(bar_mma2);
       }
       __syncwarp();
@@ -510,17 +585,23 @@ cudaError_t launch_mlp_tc(const srcv_shape& s, const float* cur, const Workspace
   const long long num_tiles = (long long)s.B * s.D * tiles_x * tiles_y;
   const int grid = (int)(num_tiles < sms ? num_tiles : sms);
   const float4* src4 = reinterpret_cast<const float4*>(ws.src_c4);
-  if (per_pixel) {
-    err = cudaFuncSetAttribute(mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    if (err != cudaSuccess) return err;
-    mlp_tc_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(s, cur, src4, ws.views, ws.frames, planes,
-                                                               image, cost, mask, num_tiles);
-  } else {
-    err = cudaFuncSetAttribute(mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    if (err != cudaSuccess) return err;
-    mlp_tc_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(s, cur, src4, ws.views, ws.frames, planes,
-                                                                image, cost, mask, num_tiles);
-  }
+  const float4* cur4 = reinterpret_cast<const float4*>(ws.cur_c4);
+  (void)cur;
+#define SRCV_TC_LAUNCH(PP, TW_, TH_)                                                                  \
+  do {                                                                                                \
+    err = cudaFuncSetAttribute(mlp_tc_kernel<PP, TW_, TH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                               (int)kSmemBytes);                                                      \
+    if (err != cudaSuccess) return err;                                                               \
+    mlp_tc_kernel<PP, TW_, TH_><<<grid, kThreads, kSmemBytes, stream>>>(                              \
+        s, cur4, src4, ws.views, ws.frames, planes, image, cost, mask, num_tiles);                    \
+  } while (0)
+#define SRCV_TC_SIZES(PP)                                                   \
+  if (s.W == 160 && s.H == 120) SRCV_TC_LAUNCH(PP, 160, 120);               \
+  else if (s.W == 128 && s.H == 96) SRCV_TC_LAUNCH(PP, 128, 96);            \
+  else SRCV_TC_LAUNCH(PP, 0, 0)
+  if (per_pixel) { SRCV_TC_SIZES(true); } else { SRCV_TC_SIZES(false); }
+#undef SRCV_TC_SIZES
+#undef SRCV_TC_LAUNCH
   note_launch();
   err = cudaGetLastError();
   if (err != cudaSuccess) return err;

@@ -73,8 +73,9 @@ __device__ void view_params(const float* __restrict__ Kmat, const float* __restr
 
 __global__ void __launch_bounds__(256)
 prep_kernel(srcv_shape s, srcv_cameras cams, srcv_planes pl, const float* __restrict__ src,
-            float* __restrict__ planes_ws, ViewParams* __restrict__ views,
-            FrameParams* __restrict__ frames, float* __restrict__ src_c4) {
+            const float* __restrict__ cur, float* __restrict__ planes_ws,
+            ViewParams* __restrict__ views, FrameParams* __restrict__ frames,
+            float* __restrict__ src_c4, float* __restrict__ cur_c4) {
   const long long nv = (long long)s.B * s.K;
   const long long nf = s.B;
   const long long np = (pl.mode == SRCV_PLANES_FROM_RANGE) ? (long long)s.B * s.D : 0;
@@ -97,6 +98,20 @@ prep_kernel(srcv_shape s, srcv_cameras cams, srcv_planes pl, const float* __rest
     return;
   }
   i -= nt;
+  const long long nc = cur_c4 ? (long long)s.B * (s.C / 4) * HW : 0;
+  if (i < nc) {
+    // same layout for the reference-frame features: (B,C/4,H,W,4)
+    const long long bj = i / HW, p = i - bj * HW;
+    const float* in = cur + bj * 4 * HW + p;
+    float4 v;
+    v.x = __ldg(in);
+    v.y = __ldg(in + HW);
+    v.z = __ldg(in + 2 * HW);
+    v.w = __ldg(in + 3 * HW);
+    reinterpret_cast<float4*>(cur_c4)[i] = v;
+    return;
+  }
+  i -= nc;
   if (i < nv) {
     const long long b = i / s.K;
     view_params(cams.src_Ks + i * 16, cams.src_extrinsics + i * 16, cams.cur_invK + b * 16,
@@ -161,26 +176,29 @@ Workspace carve_workspace(const srcv_shape& s, void* base, bool want_c4, size_t 
   if (want_c4) {
     ws.src_c4 = reinterpret_cast<float*>(
         take(sizeof(float) * (size_t)s.B * s.K * s.C * s.H * s.W));
+    ws.cur_c4 = reinterpret_cast<float*>(take(sizeof(float) * (size_t)s.B * s.C * s.H * s.W));
   }
   if (extra_bytes) ws.extra = reinterpret_cast<float*>(take(extra_bytes));
   ws.bytes = off;
-  if (!p) { ws.planes = nullptr; ws.views = nullptr; ws.frames = nullptr; ws.src_c4 = nullptr; ws.extra = nullptr; }
+  if (!p) { ws.planes = nullptr; ws.views = nullptr; ws.frames = nullptr; ws.src_c4 = nullptr; ws.cur_c4 = nullptr; ws.extra = nullptr; }
   return ws;
 }
 
 cudaError_t launch_prep(const srcv_shape& s, const srcv_cameras& cams, const srcv_planes& pl,
-                        const float* src_feats, const Workspace& ws, bool need_poses,
-                        cudaStream_t stream) {
+                        const float* src_feats, const float* cur_feats, const Workspace& ws,
+                        bool need_poses, cudaStream_t stream) {
   srcv_cameras c = cams;
   if (!need_poses) c.src_poses = nullptr;
   const long long nv = (long long)s.B * s.K;
   const long long np = (pl.mode == SRCV_PLANES_FROM_RANGE) ? (long long)s.B * s.D : 0;
   const long long nt = ws.src_c4 ? nv * (s.C / 4) * s.H * s.W : 0;
-  const long long total = nt + nv + s.B + np;
+  const long long ncur = (ws.src_c4 && ws.cur_c4) ? (long long)s.B * (s.C / 4) * s.H * s.W : 0;
+  const long long total = nt + ncur + nv + s.B + np;
   const int threads = 256;
   const long long blocks = (total + threads - 1) / threads;
-  prep_kernel<<<(unsigned)blocks, threads, 0, stream>>>(s, c, pl, src_feats, ws.planes, ws.views,
-                                                        ws.frames, ws.src_c4);
+  prep_kernel<<<(unsigned)blocks, threads, 0, stream>>>(s, c, pl, src_feats, cur_feats, ws.planes,
+                                                        ws.views, ws.frames, ws.src_c4,
+                                                        ncur ? ws.cur_c4 : nullptr);
   note_launch();
   return cudaGetLastError();
 }
