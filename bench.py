@@ -55,6 +55,27 @@ def algorithmic_bytes_per_frame(w, hero: bool, with_mask: bool) -> int:
     return b
 
 
+def binding_roof(w, hero, frames, sweep_s):
+    """The roof that actually binds: for the dot sweep the 128 B/clk/SM L1 data
+    path that every bilinear tap has to cross (4 taps x C x 4 B per (plane, view, pixel)); for the
+    hero sweep the fp16 tensor pipe (3 MMAs per product) against the measured cuBLAS bf16 rate."""
+    sm, clk = 148, 1.965e9
+    samples = frames * w.planes * w.views * w.height * w.width
+    if not hero:
+        gather_bytes = samples * 4 * w.channels * 4
+        peak = sm * 128 * clk
+        return {"resource": "l1_gather_bytes", "achieved_TBps": gather_bytes / sweep_s / 1e12,
+                "peak_TBps": peak / 1e12, "frac": gather_bytes / sweep_s / peak,
+                "peak_source": "nominal 128 B/clk/SM x 148 SMs x 1.965 GHz"}
+    f_in = w.channels * (w.views + 1) + 10 * w.views + 4
+    flops = 2.0 * 3 * frames * w.planes * w.height * w.width * (f_in * 128 + 128 * 128)
+    p = ROOT / "MEASURED_PEAKS.json"
+    peak = float(json.loads(p.read_text())["bf16_tflops"]) * 1e12 if p.is_file() else 1.59e15
+    return {"resource": "tensor_f16_flops(3 MMAs per product)", "achieved_TFLOPs": flops / sweep_s / 1e12,
+            "peak_TFLOPs": peak / 1e12, "frac": flops / sweep_s / peak,
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops (cuBLAS burst)"}
+
+
 def load_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.is_file():
@@ -142,12 +163,38 @@ def cpu_port_step(w, tup, weights):
                          sampler="aten")
 
 
+def pick_cpu_threads(w) -> int:
+    """The port is ATen ops on ~20 k-pixel tensors: on a many-core host more threads can be
+    SLOWER (128 threads: 0.44 frames/s, 16 threads: >5 on the same box).  Probe a few thread
+    counts on a 4-plane slice of one frame and keep the fastest, so the baseline is the best
+    the host can do, not an oversubscribed one."""
+    import dataclasses
+    from oracle import costvolume_oracle as O
+    from simplerecon_b200.synthetic import make_workload_tuple, mlp_state
+    cores = os.cpu_count() or 1
+    cands = sorted({c for c in (4, 8, 16, 32, 64, cores) if c <= cores})
+    small = dataclasses.replace(w, planes=4)
+    tup = make_workload_tuple(w, batch=1)
+    weights = O.mlp_weights_from_state_dict(mlp_state(w.views, w.channels)) if w.kind == "mlp" else None
+    best, best_t = cands[0], float("inf")
+    with torch.inference_mode():
+        for c in cands:
+            torch.set_num_threads(c)
+            cpu_port_step(small, tup, weights)
+            t0 = time.perf_counter()
+            cpu_port_step(small, tup, weights)
+            dt = time.perf_counter() - t0
+            if dt < best_t:
+                best, best_t = c, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def time_cpu_port(w, frames: int, min_seconds: float, max_reps: int):
     """Returns (frames_per_s, cores, sample description)."""
     from oracle import costvolume_oracle as O
     from simplerecon_b200.synthetic import make_workload_tuple, mlp_state
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores = pick_cpu_threads(w)
     tup = make_workload_tuple(w, batch=frames)
     weights = O.mlp_weights_from_state_dict(mlp_state(w.views, w.channels)) if w.kind == "mlp" else None
     with torch.inference_mode():
@@ -158,7 +205,8 @@ def time_cpu_port(w, frames: int, min_seconds: float, max_reps: int):
             cpu_port_step(w, tup, weights)
             best = min(best, time.perf_counter() - t0)
             reps += 1
-    return frames / best, cores, f"{frames} frame(s) of {w.name}, best of {reps} after 1 warm-up"
+    return frames / best, cores, (f"{frames} frame(s) of {w.name}, best of {reps} after 1 warm-up, "
+                                  f"{cores} of {os.cpu_count()} host threads (fastest of a probe)")
 
 
 def run_reference_arm(args, w):
@@ -169,8 +217,7 @@ def run_reference_arm(args, w):
         return
     from oracle import costvolume_oracle as O
     from simplerecon_b200.synthetic import make_workload_tuple, mlp_state
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores = pick_cpu_threads(w)
     frames = 1 if w.kind == "mlp" else min(w.batch, 2)     # bounded sample of one batch
     tup = make_workload_tuple(w, batch=frames)
     weights = O.mlp_weights_from_state_dict(mlp_state(w.views, w.channels)) if w.kind == "mlp" else None
@@ -182,7 +229,8 @@ def run_reference_arm(args, w):
             cpu_port_step(w, tup, weights)
         dt = time.perf_counter() - t0
     fps = frames * args.steps / dt
-    sample = f"{frames} frame(s) per step of {w.name} (bounded sample of the batch)"
+    sample = (f"{frames} frame(s) per step of {w.name} (bounded sample of the batch), "
+              f"{cores} of {os.cpu_count()} host threads (fastest of a probe)")
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
@@ -294,38 +342,32 @@ def main():
         sampler.active.clear()
         prep_ms, sweep_ms, nrec = _native.profile_end()
 
-        # ---- e2e: pinned host inputs -> H2D -> sweep -> D2H ------------------
-        pin = [{k: v.pin_memory() for k, v in s.items()} for s in sets_host[:2]]
+        # ---- e2e: pinned host inputs -> H2D -> sweep -> D2H, through HostStreamer ------
+        from simplerecon_b200.pipeline import HostStreamer
+        pin = [{k: v.pin_memory() for k, v in s_.items()} for s_ in sets_host[:3]]
         h2d = sum(v.numel() * v.element_size() for v in pin[0].values())
-        out_host = None
-
-        def e2e_step(i):
-            nonlocal out_host
-            hd = {k: v.to(dev, non_blocking=True) for k, v in pin[i % 2].items()}
-            res = mgr(**hd, **kw)
-            keep = [res[0], res[1]] + ([res[3]] if res[3] is not None else [])
-            if out_host is None:
-                out_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in keep]
-            for dst, src in zip(out_host, keep):
-                dst.copy_(src, non_blocking=True)
-            return keep
-
-        for i in range(3):
-            e2e_step(i)
-        torch.cuda.synchronize()
-        d2h = sum(t.numel() * t.element_size() for t in out_host)
+        streamer = HostStreamer(mgr, dev, return_mask=hero)
+        outs = list(streamer.run(pin[i % 3] for i in range(4)))          # warm-up
+        d2h = sum(t.numel() * t.element_size() for t in outs[-1])
         e2e_steps = max(5, min(args.steps, 50))
         sharding.barrier()
         torch.cuda.synchronize()
         sampler.active.set()
+        t_wall0 = time.perf_counter()
         e0.record()
-        for i in range(e2e_steps):
-            e2e_step(i)
+        n_out = 0
+        for host_res in streamer.run(pin[i % 3] for i in range(e2e_steps)):
+            n_out += 1
         e1.record()
         torch.cuda.synchronize()
+        t_wall = time.perf_counter() - t_wall0
         sampler.active.clear()
         sharding.barrier()
-        e2e_ms = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
+        assert n_out == e2e_steps
+        # device time between the first H2D and the last D2H (events on the default stream
+        # bracket the streamer's three streams through the synchronising yields) vs wall clock:
+        # report the larger so host-side stalls are not hidden
+        e2e_ms = sharding.max_over_ranks(max(e0.elapsed_time(e1), 1e3 * t_wall), dev)
 
     clocks = sampler.summary()
     frames_total = per_gpu * world * args.steps
@@ -343,8 +385,9 @@ def main():
         "sweep_us_per_launch": sweep_avg_s * 1e6, "prep_us_per_launch": prep_ms * 1e3 / max(nrec, 1),
         "sweep_share_of_step": (sweep_ms / max(nrec, 1)) / (ms_local / args.steps),
         "peak_source": peak_src,
-        "note": ("HBM fraction as the metric demands; the sweep is bound by on-chip gather "
-                 "bandwidth / FP32 issue (dot) or the MLP contraction (hero), see DESIGN.md"),
+        "binding": binding_roof(w, hero, per_gpu, sweep_avg_s),
+        "note": ("HBM fraction as the metric demands; the sweep is bound on chip (L1 gather "
+                 "bandwidth for dot, tensor + SIMT issue for hero) — see `binding` and DESIGN.md"),
     }
 
     line = {
@@ -355,7 +398,7 @@ def main():
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                "mode": "serial: pinned H2D -> forward -> D2H on one stream"},
+                "mode": "HostStreamer: H2D(i+1) || sweep(i) || D2H(i-1) on three streams, pinned host buffers"},
         "gpu_launches": launches,
         "clocks": clocks,
         "kernel_variant": variant,

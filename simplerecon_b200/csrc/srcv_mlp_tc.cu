@@ -5,22 +5,23 @@
 // K = 7 source views, C = 16 channels, MLP 202 -> 128 -> 128 -> 1.
 //
 // One persistent CTA per SM walks over row tiles; a tile = 128 rows = a 16 x 8 block of
-// pixels at one depth plane.  Per tile
-//   1. sixteen producer warps (four threads per row: views {0,1} | {2,3} | {4,5} | {6 + the
-//      view-independent channels}) project, gather (chunk-planar copy of the source
-//      features, csrc/srcv_prep.cu) and build the row's 202 metadata channels in
-//      registers, split every value into an fp16 (hi, lo) pair and write them straight
-//      into TENSOR MEMORY as the A operand (tcgen05.st) — the (B,F,H,W) / (B*D,H,W,F)
-//      tensors the reference materialises exist only as 208 TMEM columns per row;
-//   2. one thread issues layer 1 as 13 x 3 tcgen05.mma (A from TMEM, weights from
-//      shared memory, fp32 accumulator in TMEM):  A_hi W_hi + A_hi W_lo + A_lo W_hi;
-//   3. four epilogue warps (thread = row) read the accumulator, add bias, LeakyReLU,
-//      split to fp16 (hi, lo) again and write the layer-2 A operand back to TMEM;
-//   4. layer 2 as 8 x 3 tcgen05.mma into the same accumulator columns;
-//   5. the epilogue warps apply bias + LeakyReLU and the 128 -> 1 layer as a dot in
-//      registers and store the cost.
-// The stages are chained by mbarriers (tcgen05.commit for MMA completion), so the
-// producers already build tile t+1 while tile t is in its MMA / epilogue stages.
+// pixels at one depth plane.  Sixteen "row worker" warps (four threads per row) and one
+// MMA-issuing thread run this per-tile pipeline:
+//   1. the workers project, gather (chunk-planar copies of the features, csrc/srcv_prep.cu)
+//      and build the row's 202 metadata channels in registers, split every value into an
+//      fp16 (hi, lo) pair and write them straight into TENSOR MEMORY as the A operand
+//      (tcgen05.st) — the (B,F,H,W) / (B*D,H,W,F) tensors the reference materialises exist
+//      only as 208 TMEM columns per row;
+//   2. layer 1 = 13 x 3 tcgen05.mma (A from TMEM, weights from shared memory, fp32
+//      accumulator in TMEM):  A_hi W_hi + A_hi W_lo + A_lo W_hi;
+//   3. the workers read the accumulator (each its 32 columns), add bias, LeakyReLU, split to
+//      fp16 (hi, lo) again and write the layer-2 A operand back to TMEM;
+//   4. layer 2 = 8 x 3 tcgen05.mma into the same accumulator columns;
+//   5. the workers apply bias + LeakyReLU and the 128 -> 1 layer as partial dots, reduced in
+//      a fixed order through shared memory, and store the cost.
+// Stages are chained by mbarriers (tcgen05.commit for MMA completion).  A worker builds the
+// first K block of tile t+1 while tile t's layer-1 MMAs run and the second one while its
+// layer-2 MMAs run, so the tensor pipe and the SIMT pipes overlap.
 // Weights (both layers, hi and lo, 168 KB) stay resident in shared memory for the
 // CTA's lifetime, laid out as K-major no-swizzle core matrices by the pack kernel.
 //
@@ -57,18 +58,15 @@ static_assert(kColA2Lo + kK2 / 2 <= kTmemCols, "TMEM budget");
 // out of the fp16 subnormal range; the epilogues fold the 1/16 into their bias FMA.
 constexpr float kWScale = 16.0f, kWUnscale = 1.0f / 16.0f;
 
-constexpr int kProdWarps = 16, kEpiWarps = 4;   // 4 producer threads per row
-constexpr int kMmaWarp = kProdWarps + kEpiWarps;
-// Register allocation is per 4-warp group, so the CTA is launched as 24 warps x 80
-// registers (61440 of the SM's 65536): warps 0-15 producers, 16-19 epilogue, 20 the MMA
-// issuer, 21-23 idle fillers of its warpgroup.  setmaxnreg then re-balances WITHIN that
-// launch allocation (it cannot draw on the SM's unallocated registers): the epilogue group
-// drops to 56, the MMA group to 40, and the four producer groups grow to 96.
-constexpr int kThreads = (kProdWarps + kEpiWarps + 4) * 32;
-constexpr int kRegsLaunch = 80, kRegsProd = 96, kRegsEpi = 56, kRegsMma = 40;
-static_assert(kThreads * kRegsLaunch <= 65536, "launch allocation");
-static_assert(kProdWarps * 32 * kRegsProd + kEpiWarps * 32 * kRegsEpi + 128 * kRegsMma <= kThreads * kRegsLaunch,
-              "setmaxnreg budget must fit the CTA's launch allocation");
+// 16 "row worker" warps: four threads per row (quarter q = warp / 4).  Every worker is
+// producer AND epilogue of its rows — it builds K blocks {2q, 2q+1} of the A operand and
+// post-processes accumulator columns [32q, 32q+32) — so the epilogues, which sit on the
+// per-tile critical path MMA1 -> epi1 -> MMA2 -> epi2, get all 16 warps' issue slots
+// instead of competing with separate producer warps.  Warp 16 issues the MMAs; warps
+// 17-19 only pad the block to a 4-warp allocation unit (20 warps x 96 registers).
+constexpr int kWorkWarps = 16, kMmaWarp = 16;
+constexpr int kThreads = 20 * 32;
+constexpr int kWorkers = kWorkWarps * 32;
 
 // shared memory image (bytes)
 constexpr uint32_t kW1Bytes = kN * kK1 * 2, kW2Bytes = kN * kK2 * 2;   // one of (hi, lo)
@@ -77,7 +75,8 @@ constexpr uint32_t kOffW1Hi = 0, kOffW1Lo = kW1Bytes, kOffW2Hi = 2 * kW1Bytes,
 constexpr uint32_t kVecFloats = 3 * kN + 4;   // b1 | b2 | w3 | b3
 constexpr uint32_t kOffBar = kOffVec + kVecFloats * 4;
 constexpr uint32_t kOffFlag = kOffBar + 8 * 8;            // 8 mbarrier slots
-constexpr uint32_t kSmemBytes = kOffFlag + 2 * 4 * kRows; // mask bits [parity][quarter][row]
+constexpr uint32_t kOffPart = kOffFlag + 2 * 4 * kRows;   // mask bits [parity][quarter][row]
+constexpr uint32_t kSmemBytes = kOffPart + 2 * 4 * kRows * 4;  // layer-3 partial dots [parity][quarter][row]
 // image = [W1hi | W1lo | W2hi | W2lo | b1 b2 w3 b3] exactly as it sits in shared memory
 constexpr uint32_t kImageBytes = kOffBar;
 
@@ -276,6 +275,68 @@ __device__ __forceinline__ TileCoord tile_coord(long long id, int D, int tiles_x
   return t;
 }
 
+// Row context of one tile for one worker thread (what the K blocks and the final store need).
+struct TileRow {
+  RowCtx rc;
+  float cx, cy, cz;   // n_cur
+  int b, d, p;        // frame, plane, pixel index (clamped into the map)
+  bool active;        // row maps to a real pixel (partial tiles at the right/bottom border)
+};
+
+template <bool PER_PIXEL>
+__device__ __forceinline__ void make_tile_row(long long id, int rx, int ry, int W, int H, int HW, int D,
+                                              int tiles_x, int tiles_xy, const Centre& ctr,
+                                              const FrameParams* __restrict__ frames,
+                                              const float* __restrict__ planes, TileRow& tr) {
+  const TileCoord t = tile_coord(id, D, tiles_x, tiles_xy);
+  tr.b = t.b; tr.d = t.d;
+  tr.active = (t.x0 + rx < W) && (t.y0 + ry < H);
+  const int ox = min(t.x0 + rx, W - 1), oy = min(t.y0 + ry, H - 1);
+  tr.p = oy * W + ox;
+  const float pxc = (float)ox + 0.5f, pyc = (float)oy + 0.5f;
+  RowCtx& rc = tr.rc;
+  rc.dval = PER_PIXEL ? __ldg(planes + ((size_t)t.b * D + t.d) * HW + tr.p) : __ldg(planes + t.b * D + t.d);
+  rc.dxc = pxc - ctr.half_w;
+  rc.dyc = pyc - ctr.half_h;
+  // rays: X = d * (invK3 p); n_cur = X / max(|X|, 1e-12)
+  const FrameParams& fp = frames[t.b];
+  const float rxv = fmaf(fp.invK[0], pxc, fmaf(fp.invK[1], pyc, fp.invK[2]));
+  const float ryv = fmaf(fp.invK[3], pxc, fmaf(fp.invK[4], pyc, fp.invK[5]));
+  const float rzv = fmaf(fp.invK[6], pxc, fmaf(fp.invK[7], pyc, fp.invK[8]));
+  rc.X = rc.dval * rxv; rc.Y = rc.dval * ryv; rc.Z = rc.dval * rzv;
+  const float ic = inv_norm(fmaf(rc.X, rc.X, fmaf(rc.Y, rc.Y, rc.Z * rc.Z)), kEpsNorm);
+  tr.cx = rc.X * ic; tr.cy = rc.Y * ic; tr.cz = rc.Z * ic;
+  const float i1 = inv_norm(fmaf(tr.cx, tr.cx, fmaf(tr.cy, tr.cy, tr.cz * tr.cz)), kEpsCos);
+  rc.cxn = tr.cx * i1; rc.cyn = tr.cy * i1; rc.czn = tr.cz * i1;
+}
+
+// K block `blk` (0..6: source view, 7: view-independent tail) of a row -> packed (hi, lo)
+template <int TW, int HWC>
+__device__ __forceinline__ unsigned build_block(TileRow& tr, int blk, const float4* __restrict__ cur4g,
+                                                const float4* __restrict__ src4,
+                                                const ViewParams* __restrict__ views, int W, int H, int HW,
+                                                const Centre& ctr, uint32_t (&hi)[13], uint32_t (&lo)[13]) {
+  float v[kBlk];
+  unsigned bits = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) tr.rc.cur4[j] = __ldg(cur4g + ((size_t)tr.b * 4 + j) * HW + tr.p);
+  if (blk < kViews) {
+    bits = view_block<TW, HWC>(tr.rc, views[tr.b * kViews + blk],
+                               src4 + ((size_t)(tr.b * kViews + blk) * 4) * HW, W, H, HW, ctr, v);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[4 * j] = tr.rc.cur4[j].x; v[4 * j + 1] = tr.rc.cur4[j].y;
+      v[4 * j + 2] = tr.rc.cur4[j].z; v[4 * j + 3] = tr.rc.cur4[j].w;
+    }
+    v[kC] = tr.rc.dval; v[kC + 1] = tr.cx; v[kC + 2] = tr.cy; v[kC + 3] = tr.cz;
+#pragma unroll
+    for (int j = kC + 4; j < kBlk; ++j) v[j] = 0.f;
+  }
+  split_block(v, hi, lo);
+  return bits;
+}
+
 template <bool PER_PIXEL, int TW, int TH>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __restrict__ src4,
@@ -285,12 +346,14 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t s_tmem_base;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  uint64_t* bar_a1_full = bars + 0;   // producers -> MMA   (256 arrivals)
-  uint64_t* bar_mma1 = bars + 1;      // layer-1 MMAs done  (commit)
-  uint64_t* bar_a2_full = bars + 2;   // epilogue -> MMA    (128 arrivals)
-  uint64_t* bar_mma2 = bars + 3;      // layer-2 MMAs done  (commit)
-  uint64_t* bar_d_free = bars + 4;    // epilogue done reading the accumulator (128 arrivals)
+  uint64_t* bar_a1_full = bars + 0;   // workers -> MMA: A1 of a tile is in TMEM      (512 arrivals)
+  uint64_t* bar_mma1 = bars + 1;      // layer-1 MMAs done                           (commit)
+  uint64_t* bar_a2_full = bars + 2;   // workers -> MMA: A2 written, D1 consumed      (512 arrivals)
+  uint64_t* bar_mma2 = bars + 3;      // layer-2 MMAs done                           (commit)
+  uint64_t* bar_d_free = bars + 4;    // workers done reading the accumulator        (512 arrivals)
+  uint64_t* bar_e2 = bars + 5;        // layer-3 partial dots are in shared memory   (512 arrivals)
   uint8_t* sflag = smem + kOffFlag;
+  float* spart = reinterpret_cast<float*>(smem + kOffPart);
   const float* svec = reinterpret_cast<const float*>(smem + kOffVec);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -305,11 +368,12 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
     for (uint32_t i = tid; i < kImageBytes / 16; i += kThreads) sdst[i] = __ldg(g + i);
   }
   if (tid == 0) {
-    mbar_init(bar_a1_full, kProdWarps * 32);
+    mbar_init(bar_a1_full, kWorkers);
     mbar_init(bar_mma1, 1);
-    mbar_init(bar_a2_full, kEpiWarps * 32);
+    mbar_init(bar_a2_full, kWorkers);
     mbar_init(bar_mma2, 1);
-    mbar_init(bar_d_free, kEpiWarps * 32);
+    mbar_init(bar_d_free, kWorkers);
+    mbar_init(bar_e2, kWorkers);
     mbar_fence_init();
   }
   if (warp == kMmaWarp) tmem_alloc(&s_tmem_base, kTmemCols);
@@ -319,111 +383,84 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
   fence_after_sync();
   const uint32_t tmem_base = s_tmem_base;
   const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  // Work split: CTA c takes tiles c, c + grid, c + 2 grid, ... of the plane-fastest tile
+  // order, i.e. at any moment the 148 CTAs sweep ~2 neighbouring pixel blocks x 64 planes of
+  // ONE frame, whose source features (39 MB) stay L2-resident.  (Measured alternatives: one
+  // contiguous range per CTA over the whole batch 2.98 ms, per frame 3.02 ms vs 2.71 ms for
+  // this interleaving at B = 8.)  Local index j -> tile id.
+  const long long tile_begin = 0;
+  const long long tile_end = (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  auto tile_id = [&](long long j) { return (long long)blockIdx.x + j * gridDim.x; };
 
-  if (warp < kProdWarps) {
-    reg_inc<kRegsProd>();
-    // =============================== producers =========================================
-    // four threads per row: quarter q builds views {2q, 2q+1}; q = 3 builds view 6 + the tail
-    const int row = tid & (kRows - 1), quarter = tid >> 7;
+  if (warp < kWorkWarps) {
+    // =============================== row workers =========================================
+    const int row = tid & (kRows - 1), q = tid >> 7;
     const int rx = row & (kTileW - 1), ry = row >> 4;
     const Centre ctr(W, H);
-    int it = 0;
-    for (long long id = blockIdx.x; id < num_tiles; id += gridDim.x, ++it) {
-      const TileCoord t = tile_coord(id, D, tiles_x, tiles_xy);
-      const int ox = min(t.x0 + rx, W - 1), oy = min(t.y0 + ry, H - 1);
-      const int p = oy * W + ox;
-      const float pxc = (float)ox + 0.5f, pyc = (float)oy + 0.5f;
-      RowCtx rc;
-      rc.dval = PER_PIXEL ? __ldg(planes + ((size_t)t.b * D + t.d) * HW + p)
-                          : __ldg(planes + t.b * D + t.d);
-      rc.dxc = pxc - ctr.half_w;
-      rc.dyc = pyc - ctr.half_h;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) rc.cur4[j] = __ldg(cur4g + ((size_t)t.b * 4 + j) * HW + p);
-      // rays: X = d * (invK3 p); n_cur = X / |X|
-      const FrameParams& fp = frames[t.b];
-      const float rxv = fmaf(fp.invK[0], pxc, fmaf(fp.invK[1], pyc, fp.invK[2]));
-      const float ryv = fmaf(fp.invK[3], pxc, fmaf(fp.invK[4], pyc, fp.invK[5]));
-      const float rzv = fmaf(fp.invK[6], pxc, fmaf(fp.invK[7], pyc, fp.invK[8]));
-      rc.X = rc.dval * rxv; rc.Y = rc.dval * ryv; rc.Z = rc.dval * rzv;
-      const float ic = inv_norm(fmaf(rc.X, rc.X, fmaf(rc.Y, rc.Y, rc.Z * rc.Z)), kEpsNorm);
-      const float cx = rc.X * ic, cy = rc.Y * ic, cz = rc.Z * ic;
-      const float i1 = inv_norm(fmaf(cx, cx, fmaf(cy, cy, cz * cz)), kEpsCos);
-      rc.cxn = cx * i1; rc.cyn = cy * i1; rc.czn = cz * i1;
-
-      const int k0 = 2 * quarter;
-      const float4* view_base = src4 + (size_t)(t.b * kViews) * 4 * HW;
-      uint32_t hi[13], lo[13];
-      unsigned bits;
-      {
-        // first block is built BEFORE the wait: it overlaps the previous tile's layer-1 MMAs
-        float v[kBlk];
-        bits = view_block<TW, HWC>(rc, views[t.b * kViews + k0], view_base + (size_t)k0 * 4 * HW, W, H, HW, ctr, v);
-        split_block(v, hi, lo);
-      }
-      // A1 is free once the previous tile's layer-1 MMAs have completed
-      mbar_wait(bar_mma1, (it & 1) ^ 1);
-      fence_after_sync();
-      store_block(lane_base, (uint32_t)(13 * k0), hi, lo);
-      {
-        float v[kBlk];
-        if (quarter < 3) {
-          bits |= view_block<TW, HWC>(rc, views[t.b * kViews + k0 + 1], view_base + (size_t)(k0 + 1) * 4 * HW, W, H, HW, ctr, v);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            v[4 * j] = rc.cur4[j].x; v[4 * j + 1] = rc.cur4[j].y; v[4 * j + 2] = rc.cur4[j].z; v[4 * j + 3] = rc.cur4[j].w;
-          }
-          v[kC] = rc.dval; v[kC + 1] = cx; v[kC + 2] = cy; v[kC + 3] = cz;
-#pragma unroll
-          for (int j = kC + 4; j < kBlk; ++j) v[j] = 0.f;
-        }
-        split_block(v, hi, lo);
-      }
-      store_block(lane_base, (uint32_t)(13 * (k0 + 1)), hi, lo);
-      sflag[((it & 1) * 4 + quarter) * kRows + row] = (uint8_t)bits;
+    const int blk0 = 2 * q, blk1 = 2 * q + 1;   // q = 3: view 6 and the tail block (7)
+    TileRow cur_row, nxt_row;
+    uint32_t hi[13], lo[13];
+    long long id = tile_begin;
+    if (id < tile_end) {
+      // prologue: the first tile's A operand (its columns are free)
+      make_tile_row<PER_PIXEL>(tile_id(id), rx, ry, W, H, HW, D, tiles_x, tiles_xy, ctr, frames, planes, cur_row);
+      unsigned bits = build_block<TW, HWC>(cur_row, blk0, cur4g, src4, views, W, H, HW, ctr, hi, lo);
+      store_block(lane_base, (uint32_t)(13 * blk0), hi, lo);
+      bits |= build_block<TW, HWC>(cur_row, blk1, cur4g, src4, views, W, H, HW, ctr, hi, lo);
+      store_block(lane_base, (uint32_t)(13 * blk1), hi, lo);
+      sflag[(0 * 4 + q) * kRows + row] = (uint8_t)bits;
       wait_st();
       fence_before_sync();
       mbar_arrive(bar_a1_full);
     }
-  } else if (warp < kMmaWarp) {
-    reg_dec<kRegsEpi>();
-    // =============================== epilogue ===========================================
-    const int row = tid - kProdWarps * 32;
-    const int rx = row & (kTileW - 1), ry = row >> 4;
     int it = 0;
-    for (long long id = blockIdx.x; id < num_tiles; id += gridDim.x, ++it) {
-      const TileCoord t = tile_coord(id, D, tiles_x, tiles_xy);
-      const int ox = t.x0 + rx, oy = t.y0 + ry;
-      const bool active = ox < W && oy < H;
-      // ---- layer-1 epilogue: bias + LeakyReLU, (hi, lo) split, A2 -> TMEM --------------
+    for (; id < tile_end; ++id, ++it) {
+      const long long nid = id + 1;
+      const bool has_next = nid < tile_end;
+      unsigned nbits = 0;
+      if (has_next) {
+        // first K block of the NEXT tile, built while this tile's layer-1 MMAs run
+        make_tile_row<PER_PIXEL>(tile_id(nid), rx, ry, W, H, HW, D, tiles_x, tiles_xy, ctr, frames, planes, nxt_row);
+        nbits = build_block<TW, HWC>(nxt_row, blk0, cur4g, src4, views, W, H, HW, ctr, hi, lo);
+      }
+      // ---- layer-1 epilogue on columns [32q, 32q+32): bias + LeakyReLU, (hi, lo), A2 -> TMEM
       mbar_wait(bar_mma1, it & 1);
       fence_after_sync();
-#pragma unroll 1
-      for (int c0 = 0; c0 < kN; c0 += 16) {
+#pragma unroll
+      for (int c0 = 32 * q; c0 < 32 * q + 32; c0 += 16) {
         uint32_t r[16];
         ld_x16(lane_base + kColD + c0, r);
         wait_ld();
-        uint32_t hi[8], lo[8];
+        uint32_t ehi[8], elo[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float2 bb = *reinterpret_cast<const float2*>(svec + c0 + 2 * j);
           const float a = leaky(fmaf(__uint_as_float(r[2 * j]), kWUnscale, bb.x));
           const float b = leaky(fmaf(__uint_as_float(r[2 * j + 1]), kWUnscale, bb.y));
-          split_pack(a, b, hi[j], lo[j]);
+          split_pack(a, b, ehi[j], elo[j]);
         }
-        st_x8(lane_base + kColA2Hi + c0 / 2, hi);
-        st_x8(lane_base + kColA2Lo + c0 / 2, lo);
+        st_x8(lane_base + kColA2Hi + c0 / 2, ehi);
+        st_x8(lane_base + kColA2Lo + c0 / 2, elo);
       }
       wait_st();
       fence_before_sync();
       mbar_arrive(bar_a2_full);
-      // ---- layer-2 epilogue: bias + LeakyReLU, 128 -> 1 dot, store -----------------------
+      // ---- the rest of the next tile's A operand (A1 is free: layer 1 of this tile is done)
+      if (has_next) {
+        store_block(lane_base, (uint32_t)(13 * blk0), hi, lo);
+        nbits |= build_block<TW, HWC>(nxt_row, blk1, cur4g, src4, views, W, H, HW, ctr, hi, lo);
+        store_block(lane_base, (uint32_t)(13 * blk1), hi, lo);
+        sflag[(((it + 1) & 1) * 4 + q) * kRows + row] = (uint8_t)nbits;
+        wait_st();
+        fence_before_sync();
+        mbar_arrive(bar_a1_full);
+      }
+      // ---- layer-2 epilogue on columns [32q, 32q+32): bias + LeakyReLU, 128 -> 1 partial dot
       mbar_wait(bar_mma2, it & 1);
       fence_after_sync();
       float acc = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < kN; c0 += 16) {
+#pragma unroll
+      for (int c0 = 32 * q; c0 < 32 * q + 32; c0 += 16) {
         uint32_t r[16];
         ld_x16(lane_base + kColD + c0, r);
         wait_ld();
@@ -439,22 +476,29 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
       }
       fence_before_sync();
       mbar_arrive(bar_d_free);
-      if (active) {
-        const int p = oy * W + ox;
-        cost[((size_t)t.b * D + t.d) * HW + p] = acc + svec[3 * kN];
-        if (mask_out != nullptr && t.d == D - 1) {
-          const uint8_t* fl = sflag + (it & 1) * 4 * kRows + row;
-          const unsigned bits = fl[0] | fl[kRows] | fl[2 * kRows] | fl[3 * kRows];
-          mask_out[(size_t)t.b * HW + p] = (bits == 3u) ? 1 : 0;
+      spart[((it & 1) * 4 + q) * kRows + row] = acc;
+      mbar_arrive(bar_e2);
+      if (q == 0) {
+        // fixed-order reduction of the four quarters (deterministic), bias, store
+        mbar_wait(bar_e2, it & 1);
+        const float* sp = spart + (it & 1) * 4 * kRows + row;
+        const float total = ((sp[0] + sp[kRows]) + sp[2 * kRows]) + sp[3 * kRows];
+        if (cur_row.active) {
+          cost[((size_t)cur_row.b * D + cur_row.d) * HW + cur_row.p] = total + svec[3 * kN];
+          if (mask_out != nullptr && cur_row.d == D - 1) {
+            const uint8_t* fl = sflag + (it & 1) * 4 * kRows + row;
+            const unsigned bits = fl[0] | fl[kRows] | fl[2 * kRows] | fl[3 * kRows];
+            mask_out[(size_t)cur_row.b * HW + cur_row.p] = (bits == 3u) ? 1 : 0;
+          }
         }
       }
+      cur_row = nxt_row;
     }
-  } else {
-    reg_dec<kRegsMma>();
+  } else if (warp == kMmaWarp) {
     // =============================== MMA issuer ==========================================
     const uint32_t sbase = smem_u32(smem);
     int it = 0;
-    for (long long id = blockIdx.x; warp == kMmaWarp && id < num_tiles; id += gridDim.x, ++it) {
+    for (long long id = tile_begin; id < tile_end; ++id, ++it) {
       mbar_wait(bar_a1_full, it & 1);          // A1 of this tile is in TMEM
       mbar_wait(bar_d_free, (it & 1) ^ 1);     // previous tile's accumulator has been read
       fence_after_sync();
