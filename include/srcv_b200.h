@@ -123,6 +123,20 @@ int32_t srcv_dot_forward_f32(const srcv_shape* shape,
                              void* workspace, size_t workspace_bytes,
                              void* stream);
 
+/* ---- single-plane warp -------------------------------------------------- *
+ * Replaces CostVolumeManager.warp_features (reference modules/cost_volume.py:139-234),
+ * the helper that MATERIALISES the warped source features of one depth plane; the
+ * sweeps above never call it (they keep the warped values in registers / TMEM), it is
+ * exported because the reference exposes it as a method.  shape->D is ignored.
+ *   depth_plane  DEVICE (B) one depth per frame, or (B,H,W) when per_pixel != 0
+ *   warped (B,K,C,H,W)  depths (B,K,H,W) = z' of the plane point in each source camera
+ *   mask   (B,K,H,W)    1.0 where z' > 0                                         */
+size_t srcv_warp_workspace_bytes(const srcv_shape* shape);
+int32_t srcv_warp_features_f32(const srcv_shape* shape, const float* src_feats,
+                               const srcv_cameras* cams, const float* depth_plane,
+                               int32_t per_pixel, float* warped, float* depths, float* mask,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- metadata-MLP volume ---------------------------------------------- *
  * Replaces FeatureVolumeManager.build_cost_volume /
  * FastFeatureVolumeManager.build_cost_volume + the argmax in forward

@@ -70,10 +70,41 @@ class CostVolumeManager(nn.Module):
         planes = torch.exp(torch.log(min_depth) + torch.log(max_depth / min_depth) * ramp)
         return planes.expand(batch_size, self.num_depth_bins, self.matching_height, self.matching_width)
 
-    def warp_features(self, *args, **kwargs):
-        raise NotImplementedError(
-            "warp_features materialises the (B,K,C,H,W) warped tensor per plane; the fused "
-            "kernels never form it.  Use build_cost_volume / forward.")
+    # -- reference :139-234 ---------------------------------------------------
+    def warp_features(self, src_feats, src_extrinsics, src_Ks, cur_invK, depth_plane_b1hw,
+                      batch_size, num_src_frames, num_feat_channels, uv_scale=None):
+        """Warps every source view to the reference view at ONE depth plane and returns
+        ``(world_points_B4N, depths, src_feat_warped, mask)`` like the reference helper.
+        This is the materialising form the fused sweeps avoid; it is kept because the
+        reference exposes it.  ``uv_scale`` is accepted and unused (the kernel works in
+        pixel coordinates)."""
+        lib = _native.load()
+        dev = src_feats.device
+        if dev.type != "cuda":
+            raise RuntimeError("simplerecon_b200 runs on CUDA (sm_100a) only; there is no CPU fallback.")
+        B, K, Cc = batch_size, num_src_frames, num_feat_channels
+        H, W = self.matching_height, self.matching_width
+        src = _f32c(src_feats, "src_feats", dev).reshape(B, K, Cc, H, W)
+        E, Ks = _f32c(src_extrinsics, "src_extrinsics", dev), _f32c(src_Ks, "src_Ks", dev)
+        invK = _f32c(cur_invK, "cur_invK", dev)
+        plane = depth_plane_b1hw
+        st = plane.stride()
+        per_pixel = not ((st[2] == 0 or H == 1) and (st[3] == 0 or W == 1))
+        plane_c = plane.contiguous().reshape(B, H * W) if per_pixel else plane[:, 0, 0, 0].contiguous()
+        shape = _native.Shape(B, K, Cc, H, W, 1)
+        cams = _native.Cameras(E.data_ptr(), None, Ks.data_ptr(), invK.data_ptr())
+        with torch.cuda.device(dev):
+            warped = torch.empty(B, K, Cc, H, W, device=dev, dtype=torch.float32)
+            depths = torch.empty(B, K, H, W, device=dev, dtype=torch.float32)
+            mask = torch.empty(B, K, H, W, device=dev, dtype=torch.float32)
+            n = lib.srcv_warp_workspace_bytes(C.byref(shape))
+            ws = torch.empty(n, device=dev, dtype=torch.uint8)
+            _native.check(lib.srcv_warp_features_f32(
+                C.byref(shape), _ptr(src), C.byref(cams), _ptr(plane_c), int(per_pixel), _ptr(warped),
+                _ptr(depths), _ptr(mask), _ptr(ws), n,
+                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        world_points_b4N = self.backprojector(depth_plane_b1hw.expand(B, 1, H, W), invK)
+        return world_points_b4N.repeat_interleave(K, dim=0), depths, warped, mask
 
     # -- reference :338-342 ---------------------------------------------------
     def indices_to_disparity(self, indices, depth_planes_bdhw):

@@ -174,6 +174,35 @@ int32_t srcv_dot_forward_f32(const srcv_shape* s, const float* cur, const float*
   return SRCV_OK;
 }
 
+size_t srcv_warp_workspace_bytes(const srcv_shape* s) {
+  if (check_shape(s) != SRCV_OK) return 0;
+  return carve_workspace(*s, nullptr, false, 0).bytes;
+}
+
+int32_t srcv_warp_features_f32(const srcv_shape* s, const float* src, const srcv_cameras* cams,
+                               const float* depth_plane, int32_t per_pixel, float* warped,
+                               float* depths, float* mask, void* workspace, size_t workspace_bytes,
+                               void* stream_) {
+  if (int32_t e = check_shape(s)) return e;
+  if (!src || !depth_plane || !warped || !depths || !mask)
+    return fail(SRCV_ERR_NULL, "warp_features pointer is NULL");
+  if (!cams || !cams->src_extrinsics || !cams->src_Ks || !cams->cur_invK)
+    return fail(SRCV_ERR_NULL, "camera block incomplete");
+  const Workspace need = carve_workspace(*s, nullptr, false, 0);
+  if (int32_t e = check_workspace(workspace, workspace_bytes, need.bytes)) return e;
+  Workspace ws = carve_workspace(*s, workspace, false, 0);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  srcv_planes pl{};
+  pl.mode = SRCV_PLANES_PER_PLANE;   // the plane comes straight from the caller
+  pl.planes = depth_plane;
+  cudaError_t err = launch_prep(*s, *cams, pl, src, nullptr, ws, false, stream);
+  if (err != cudaSuccess) return cuda_fail(err, "prep");
+  g_last_variant = "warp_plane";
+  err = launch_warp_plane(*s, src, ws, depth_plane, per_pixel != 0, warped, depths, mask, stream);
+  if (err != cudaSuccess) return cuda_fail(err, g_last_variant);
+  return SRCV_OK;
+}
+
 static int32_t check_weights(const srcv_shape* s, const srcv_mlp_weights* w) {
   if (!w) return fail(SRCV_ERR_NULL, "weights is NULL");
   if (!w->w1 || !w->b1 || !w->w2 || !w->b2 || !w->w3 || !w->b3)

@@ -225,7 +225,54 @@ void launch_fast_sized(const srcv_shape& s, dim3 grid, dim3 block, size_t smem, 
   dot_fast_kernel<PER_PIXEL, 0, 0, kTileW><<<grid, block, smem, stream>>>(s, cur, src4, views, planes, cost, lowest);
 }
 
+// --------------------------------------------------------------------------- //
+// warp only: the materialising helper the reference exposes as warp_features()  //
+// --------------------------------------------------------------------------- //
+template <bool PER_PIXEL>
+__global__ void __launch_bounds__(128)
+warp_plane_kernel(srcv_shape s, const float* __restrict__ src, const ViewParams* __restrict__ views,
+                  const float* __restrict__ plane, float* __restrict__ warped,
+                  float* __restrict__ depths, float* __restrict__ mask) {
+  const int HW = s.H * s.W;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int bk = blockIdx.y, b = bk / s.K;
+  if (p >= HW) return;
+  const Centre ctr(s.W, s.H);
+  const float dx = ((float)(p % s.W) + 0.5f) - ctr.half_w, dy = ((float)(p / s.W) + 0.5f) - ctr.half_h;
+  const float dval = PER_PIXEL ? __ldg(plane + (size_t)b * HW + p) : __ldg(plane + b);
+  const ViewParams& vp = views[bk];
+  float ax, ay, az, px, py, zp;
+  homography_point(vp.a0, dx, dy, ax, ay, az);
+  project_point(dval, ax, ay, az, vp.t[0], vp.t[1], vp.t[2], px, py, zp);
+  Taps tp;
+  bilinear_taps(px, py, s.W, s.H, ctr, tp);
+  const float w00 = (1.0f - tp.fx) * (1.0f - tp.fy), w01 = tp.fx * (1.0f - tp.fy);
+  const float w10 = (1.0f - tp.fx) * tp.fy, w11 = tp.fx * tp.fy;
+  const float* sp = src + (size_t)bk * s.C * HW + (tp.y0 * s.W + tp.x0);
+  for (int c = 0; c < s.C; ++c) {
+    const float* q = sp + (size_t)c * HW;
+    float v = 0.f;
+    if (tp.valid & 1u) v = w00 * __ldg(q);
+    if (tp.valid & 2u) v = fmaf(w01, __ldg(q + 1), v);
+    if (tp.valid & 4u) v = fmaf(w10, __ldg(q + s.W), v);
+    if (tp.valid & 8u) v = fmaf(w11, __ldg(q + s.W + 1), v);
+    warped[((size_t)bk * s.C + c) * HW + p] = v;
+  }
+  depths[(size_t)bk * HW + p] = zp;
+  mask[(size_t)bk * HW + p] = zp > 0.0f ? 1.0f : 0.0f;
+}
+
 }  // namespace
+
+cudaError_t launch_warp_plane(const srcv_shape& s, const float* src, const Workspace& ws,
+                              const float* plane, bool per_pixel, float* warped, float* depths,
+                              float* mask, cudaStream_t stream) {
+  dim3 grid((s.H * s.W + 127) / 128, s.B * s.K), block(128);
+  if (per_pixel) warp_plane_kernel<true><<<grid, block, 0, stream>>>(s, src, ws.views, plane, warped, depths, mask);
+  else warp_plane_kernel<false><<<grid, block, 0, stream>>>(s, src, ws.views, plane, warped, depths, mask);
+  note_launch();
+  return cudaGetLastError();
+}
 
 cudaError_t launch_dot_generic(const srcv_shape& s, const float* cur, const float* src,
                                const Workspace& ws, const float* planes, bool per_pixel,

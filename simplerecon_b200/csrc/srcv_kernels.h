@@ -39,6 +39,11 @@ cudaError_t launch_dot_fast(const srcv_shape& s, const float* cur, const Workspa
                             const float* planes, bool per_pixel, float* cost, float* lowest,
                             cudaStream_t stream);
 
+// single-plane warp (the reference's warp_features helper)
+cudaError_t launch_warp_plane(const srcv_shape& s, const float* src, const Workspace& ws,
+                              const float* plane, bool per_pixel, float* warped, float* depths,
+                              float* mask, cudaStream_t stream);
+
 // metadata-MLP volume
 bool mlp_generic_supported(const srcv_shape& s, const srcv_mlp_weights& w);
 size_t mlp_generic_extra_bytes(const srcv_shape& s, const srcv_mlp_weights& w);

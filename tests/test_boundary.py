@@ -94,8 +94,9 @@ def test_cpu_tensors_are_refused_not_silently_computed():
     t = make_tuple(1, 2, 6, 8, seed=1)
     with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU fallback"):
         m(**t)
-    with pytest.raises(NotImplementedError):
-        m.warp_features()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.warp_features(t["src_feats"], t["src_extrinsics"], t["src_Ks"], t["cur_invK"],
+                        torch.ones(1, 1, 6, 8), 1, 2, 16, None)
 
 
 def test_product_package_never_imports_the_oracle():

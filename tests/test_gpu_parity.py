@@ -248,3 +248,46 @@ def test_errors_on_device():
     t8 = to_device(make_tuple(1, 2, 12, 16, channels=8, seed=33), "cuda")
     with torch.no_grad(), pytest.raises(_native.SrcvError):
         m(**t8)
+
+
+def test_warp_features_helper_matches_oracle():
+    """CostVolumeManager.warp_features (reference modules/cost_volume.py:139-234): the
+    materialising single-plane helper."""
+    B, K, H, W = 2, 3, 21, 19
+    t = make_tuple(B, K, H, W, seed=44)
+    d = to_device(t, "cuda")
+    m = make_manager("dot", K, 16, H, W, 4)
+    plane = torch.full((B, 1, 1, 1), 1.7, device="cuda").expand(B, 1, H, W)
+    with torch.no_grad():
+        pts, depths, warped, mask = m.warp_features(d["src_feats"], d["src_extrinsics"], d["src_Ks"],
+                                                    d["cur_invK"], plane, B, K, 16, None)
+    assert pts.shape == (B * K, 4, H * W) and warped.shape == (B, K, 16, H, W)
+    rays = O.backproject_rays(t["cur_invK"], H, W)
+    px, py, zp = O.project(1.7 * rays, t["src_Ks"], t["src_extrinsics"])
+    ow = O.sample_bilinear_zeros(t["src_feats"], px, py).reshape(B, K, 16, H, W)
+    assert (warped.cpu() - ow).abs().max().item() <= 5e-5 * float(ow.abs().max())
+    assert torch.allclose(depths.cpu().reshape(B, K, -1), zp, rtol=1e-5, atol=1e-6)
+    assert torch.equal(mask.cpu().reshape(B, K, -1), (zp > 0).float())
+    assert torch.allclose(pts.cpu().reshape(B, K, 4, -1)[:, 0, :3], 1.7 * rays, rtol=1e-5, atol=1e-6)
+    # per-pixel plane
+    g = torch.Generator().manual_seed(3)
+    pp = (0.5 + 3 * torch.rand(B, 1, H, W, generator=g))
+    with torch.no_grad():
+        _, depths2, warped2, _ = m.warp_features(d["src_feats"], d["src_extrinsics"], d["src_Ks"],
+                                                 d["cur_invK"], pp.cuda(), B, K, 16, None)
+    px, py, zp = O.project(pp.reshape(B, 1, -1) * rays, t["src_Ks"], t["src_extrinsics"])
+    ow = O.sample_bilinear_zeros(t["src_feats"], px, py).reshape(B, K, 16, H, W)
+    assert (warped2.cpu() - ow).abs().max().item() <= 5e-5 * float(ow.abs().max())
+
+
+def test_host_streamer_matches_direct_calls():
+    from simplerecon_b200.pipeline import HostStreamer
+    m = make_manager("dot", 3, 16, 24, 32, 6)
+    batches = [{k: v.pin_memory() for k, v in make_tuple(2, 3, 24, 32, seed=60 + i).items()} for i in range(5)]
+    st = HostStreamer(m, "cuda")
+    got = [[t.clone() for t in out] for out in st.run(batches)]
+    assert len(got) == 5
+    with torch.inference_mode():
+        for b, out in zip(batches, got):
+            cost, lowest, _, _ = m(**to_device(b, "cuda"))
+            assert torch.equal(out[0], cost.cpu()) and torch.equal(out[1], lowest.cpu())
