@@ -245,7 +245,9 @@ def run_reference_arm(args, w):
 
 def workload_config(w, batch_per_gpu, world, l2_note):
     return {
-        "workload": w.name, "matching": w.kind, "frame": f"{4 * w.width}x{4 * w.height}",
+        "workload": w.name, "matching": w.kind,
+        "frame": "n/a (stress: feature map given directly)" if w.name.startswith("stress")
+        else f"{4 * w.width}x{4 * w.height}",
         "feature_map": f"{w.width}x{w.height}", "planes": w.planes, "src_views": w.views,
         "channels": w.channels, "batch_per_gpu": batch_per_gpu, "global_batch": batch_per_gpu * world,
         "parallelism": f"frame-sharded x{world} (no data-path collective)", "l2": l2_note,
@@ -267,8 +269,8 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
-    from simplerecon_b200.synthetic import CONFIGS, make_workload_tuple, mlp_state
-    w = next(c for c in CONFIGS if c.name.startswith(args.workload))
+    from simplerecon_b200.synthetic import CONFIGS, STRESS, make_workload_tuple, mlp_state
+    w = next(c for c in CONFIGS + STRESS if c.name.startswith(args.workload))
     if args.impl == "reference":
         run_reference_arm(args, w)
         return

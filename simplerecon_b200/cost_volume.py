@@ -34,7 +34,10 @@ def _f32c(t: Tensor, name: str, device) -> Tensor:
         raise ValueError(f"{name} must be float32 (got {t.dtype}); the fused path is fp32-only")
     if t.device != device:
         raise ValueError(f"{name} is on {t.device}, expected {device}")
-    return t.contiguous()
+    t = t.contiguous()
+    if t.data_ptr() % 16 != 0:      # the kernels use 16-byte vector loads
+        t = t.clone()
+    return t
 
 
 class CostVolumeManager(nn.Module):

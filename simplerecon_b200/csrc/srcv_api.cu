@@ -59,6 +59,8 @@ static int32_t check_common(const srcv_shape* s, const float* cur, const float* 
                             bool need_poses) {
   if (int32_t e = check_shape(s)) return e;
   if (!cur || !src || !cost) return fail(SRCV_ERR_NULL, "cur_feats/src_feats/cost is NULL");
+  if (((reinterpret_cast<uintptr_t>(cur) | reinterpret_cast<uintptr_t>(src)) & 15u) != 0)
+    return fail(SRCV_ERR_UNSUPPORTED, "cur_feats / src_feats must be 16-byte aligned");
   if (!cams || !cams->src_extrinsics || !cams->src_Ks || !cams->cur_invK)
     return fail(SRCV_ERR_NULL, "camera block incomplete");
   if (need_poses && !cams->src_poses) return fail(SRCV_ERR_NULL, "src_poses is NULL");
@@ -152,7 +154,7 @@ int32_t srcv_dot_forward_f32(const srcv_shape* s, const float* cur, const float*
   const Workspace need = carve_workspace(*s, nullptr, dot_fast_supported(*s), 0);
   if (int32_t e = check_workspace(workspace, workspace_bytes, need.bytes)) return e;
   Workspace ws = carve_workspace(*s, workspace, dot_fast_supported(*s), 0);
-  if (!fast) ws.src_c4 = nullptr;  // skip the chunk-planar copies
+  if (!fast) { ws.src_c4 = nullptr; ws.tile_done = nullptr; }  // skip the chunk-planar copies
   ws.cur_c4 = nullptr;             // the dot kernel keeps the reference features in registers
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ProfRecord* pr = prof_next();
@@ -246,6 +248,7 @@ int32_t srcv_mlp_forward_f32(const srcv_shape* s, const float* cur, const float*
   if (int32_t e = check_workspace(workspace, workspace_bytes, need.bytes)) return e;
   Workspace ws = carve_workspace(*s, workspace, c4, extra);
   if (!tc) ws.src_c4 = nullptr;  // skip the chunk-planar copy
+  ws.tile_done = nullptr;        // only the dot sweep uses the tile counters
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ProfRecord* pr = prof_next();
   if (pr) cudaEventRecord(pr->e[0], stream);

@@ -120,7 +120,7 @@ template <bool PER_PIXEL, int TW, int TH, int kTileW>
 __global__ void __launch_bounds__(kFastWarps * 32)
 dot_fast_kernel(srcv_shape s, const float* __restrict__ cur, const float4* __restrict__ src4,
                 const ViewParams* __restrict__ views, const float* __restrict__ planes,
-                float* __restrict__ cost, float* __restrict__ lowest) {
+                float* __restrict__ cost, float* __restrict__ lowest, unsigned* __restrict__ tile_done) {
   extern __shared__ float sview[];  // K * 12
   const int b = blockIdx.y;
   const int W = TW ? TW : s.W, H = TH ? TH : s.H, HW = W * H, K = s.K;
@@ -133,8 +133,7 @@ dot_fast_kernel(srcv_shape s, const float* __restrict__ cur, const float4* __res
   const int tiles_x = (W + kTileW - 1) / kTileW;
   const int ox_raw = (blockIdx.x % tiles_x) * kTileW + (lane & (kTileW - 1));
   const int oy_raw = ((blockIdx.x / tiles_x) * kFastWarps + (threadIdx.x >> 5)) * kTileH + lane / kTileW;
-  const bool active = ox_raw < W && oy_raw < H;
-  if (__ballot_sync(0xffffffffu, active) == 0u) return;  // whole warp outside the map
+  const bool active = ox_raw < W && oy_raw < H;   // idle lanes / warps shadow a real pixel
   const int ox = min(ox_raw, W - 1), oy = min(oy_raw, H - 1);  // idle lanes shadow a real pixel
   // planes handled by this CTA: [d_begin, d_end)
   const int dper = (s.D + gridDim.z - 1) / gridDim.z;
@@ -206,23 +205,47 @@ dot_fast_kernel(srcv_shape s, const float* __restrict__ cur, const float4* __res
     }
   }
   if (fuse_argmax && active) lowest[(size_t)b * HW + p] = best_d;
+  if (gridDim.z > 1 && lowest != nullptr) {
+    // Plane loop split over gridDim.z CTAs: the LAST CTA of this pixel tile to finish
+    // (counter zeroed by the prep pass) reduces the whole plane column it finds in L2 — the
+    // argmax stays fused without a second launch.
+    __shared__ unsigned s_last;
+    __threadfence();                       // this CTA's cost values are visible device-wide
+    __syncthreads();
+    if (threadIdx.x == 0)
+      s_last = (atomicAdd(tile_done + (size_t)b * gridDim.x + blockIdx.x, 1u) == gridDim.z - 1) ? 1u : 0u;
+    __syncthreads();
+    if (s_last && active) {
+      __threadfence();
+      const float* c = cost + (size_t)b * s.D * HW + p;
+      float bv = 0.f, bd = 0.f;
+#pragma unroll 8
+      for (int d = 0; d < s.D; ++d) {
+        const float v = __ldcg(c + (size_t)d * HW);   // L2, never a stale L1 line
+        const float dv = PER_PIXEL ? __ldg(planes + ((size_t)b * s.D + d) * HW + p) : __ldg(planes + b * s.D + d);
+        argmax_update(v, dv, bv, bd, d == 0);
+      }
+      lowest[(size_t)b * HW + p] = bd;
+    }
+  }
 }
 
 template <bool PER_PIXEL, int kTileW>
 void launch_fast_sized(const srcv_shape& s, dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                        const float* cur, const float4* src4, const ViewParams* views,
-                       const float* planes, float* cost, float* lowest) {
+                       const float* planes, float* cost, float* lowest, unsigned* tile_done) {
 #define SRCV_SIZED(TW_, TH_)                                                                   \
   if (s.W == TW_ && s.H == TH_) {                                                              \
-    dot_fast_kernel<PER_PIXEL, TW_, TH_, kTileW><<<grid, block, smem, stream>>>(s, cur, src4, views,   \
-                                                                        planes, cost, lowest); \
+    dot_fast_kernel<PER_PIXEL, TW_, TH_, kTileW><<<grid, block, smem, stream>>>(                 \
+        s, cur, src4, views, planes, cost, lowest, tile_done);                                 \
     return;                                                                                    \
   }
   SRCV_SIZED(160, 120)  // 640x480 frames (BASELINE configs)
   SRCV_SIZED(128, 96)   // 512x384 frames (the reference's default, options.py:70-71)
   SRCV_SIZED(64, 48)    // 256x192 frames (BASELINE config 0)
 #undef SRCV_SIZED
-  dot_fast_kernel<PER_PIXEL, 0, 0, kTileW><<<grid, block, smem, stream>>>(s, cur, src4, views, planes, cost, lowest);
+  dot_fast_kernel<PER_PIXEL, 0, 0, kTileW><<<grid, block, smem, stream>>>(s, cur, src4, views, planes, cost,
+                                                                          lowest, tile_done);
 }
 
 // --------------------------------------------------------------------------- //
@@ -298,8 +321,8 @@ cudaError_t launch_dot_fast(const srcv_shape& s, const float* cur, const Workspa
                             cudaStream_t stream) {
   // Split the plane loop across CTAs until there are ~64 warps per SM to schedule (the
   // sweep is latency-bound at low occupancy and smaller CTAs balance better: measured
-  // 428 -> 370 us at B = 4); a split sweep cannot fuse the argmax and runs it as a
-  // separate pass over the L2-resident volume.
+  // 428 -> 370 us at B = 4); the argmax of a split sweep is done by the last CTA of each
+  // pixel tile to finish (see the kernel).
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -320,18 +343,24 @@ cudaError_t launch_dot_fast(const srcv_shape& s, const float* cur, const Workspa
   dim3 grid(tiles_x * tiles_y, s.B, d_split), block(kFastWarps * 32);
   const size_t smem = sizeof(float) * kViewFloats * s.K;
   const float4* src4 = reinterpret_cast<const float4*>(ws.src_c4);
+  unsigned* done = ws.tile_done;
+  if (d_split > 1 && lowest && (done == nullptr || (size_t)grid.x * s.B > ws.tile_done_count))
+    return cudaErrorInvalidValue;
   if (tile_w == 32) {
-    if (per_pixel) launch_fast_sized<true, 32>(s, grid, block, smem, stream, cur, src4, ws.views, planes, cost, lowest);
-    else launch_fast_sized<false, 32>(s, grid, block, smem, stream, cur, src4, ws.views, planes, cost, lowest);
+    if (per_pixel) launch_fast_sized<true, 32>(s, grid, block, smem, stream, cur, src4, ws.views, planes, cost, lowest, done);
+    else launch_fast_sized<false, 32>(s, grid, block, smem, stream, cur, src4, ws.views, planes, cost, lowest, done);
   } else {
-    if (per_pixel) launch_fast_sized<true, 16>(s, grid, block, smem, stream, cur, src4, ws.views, planes, cost, lowest);
-    else launch_fast_sized<false, 16>(s, grid, block, smem, stream, cur, src4, ws.views, planes, cost, lowest);
+    if (per_pixel) launch_fast_sized<true, 16>(s, grid, block, smem, stream, cur, src4, ws.views, planes, cost, lowest, done);
+    else launch_fast_sized<false, 16>(s, grid, block, smem, stream, cur, src4, ws.views, planes, cost, lowest, done);
   }
   note_launch();
-  cudaError_t err = cudaGetLastError();
-  if (err != cudaSuccess) return err;
-  if (d_split > 1 && lowest) err = launch_argmax(s, cost, planes, per_pixel, lowest, stream);
-  return err;
+  return cudaGetLastError();
+}
+
+size_t dot_fast_tile_counters(const srcv_shape& s) {
+  // upper bound over both warp-tile shapes (16x4- and 32x2-pixel CTAs)
+  const size_t a = (size_t)((s.W + 15) / 16) * ((s.H + 3) / 4), b = (size_t)((s.W + 31) / 32) * ((s.H + 1) / 2);
+  return (size_t)s.B * (a > b ? a : b);
 }
 
 }  // namespace srcv

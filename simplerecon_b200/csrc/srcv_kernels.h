@@ -16,6 +16,8 @@ struct Workspace {
   FrameParams* frames;  // (B)
   float* src_c4;        // (B,K,C/4,H,W,4) chunk-planar copy of src_feats, or nullptr
   float* cur_c4;        // (B,C/4,H,W,4) chunk-planar copy of cur_feats, or nullptr
+  unsigned* tile_done;  // per (frame, pixel tile) completion counters, zeroed by the prep pass
+  size_t tile_done_count;
   float* extra;         // variant-specific scratch, or nullptr
   size_t bytes;         // total bytes needed
 };
@@ -35,6 +37,7 @@ cudaError_t launch_dot_generic(const srcv_shape& s, const float* cur, const floa
                                const Workspace& ws, const float* planes, bool per_pixel,
                                float* cost, float* lowest, cudaStream_t stream);
 bool dot_fast_supported(const srcv_shape& s);
+size_t dot_fast_tile_counters(const srcv_shape& s);
 cudaError_t launch_dot_fast(const srcv_shape& s, const float* cur, const Workspace& ws,
                             const float* planes, bool per_pixel, float* cost, float* lowest,
                             cudaStream_t stream);

@@ -75,43 +75,45 @@ __global__ void __launch_bounds__(256)
 prep_kernel(srcv_shape s, srcv_cameras cams, srcv_planes pl, const float* __restrict__ src,
             const float* __restrict__ cur, float* __restrict__ planes_ws,
             ViewParams* __restrict__ views, FrameParams* __restrict__ frames,
-            float* __restrict__ src_c4, float* __restrict__ cur_c4) {
+            float* __restrict__ src_c4, float* __restrict__ cur_c4,
+            unsigned* __restrict__ tile_done, long long n_done) {
   const long long nv = (long long)s.B * s.K;
   const long long nf = s.B;
   const long long np = (pl.mode == SRCV_PLANES_FROM_RANGE) ? (long long)s.B * s.D : 0;
   const long long HW = (long long)s.H * s.W;
   const long long nt = src_c4 ? nv * (s.C / 4) * HW : 0;
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nt) {
-    // NCHW -> chunk-planar (B,K,C/4,H,W,4): thread = one (view, chunk, pixel).  Reads
-    // (4 channel planes) and the float4 write are both coalesced across the warp.
-    const long long nch = s.C / 4;
-    const long long bkj = i / HW, p = i - bkj * HW;      // bkj = (b*K + k)*nch + j
-    const float* in = src + bkj * 4 * HW + p;            // channel 4j of view (b,k)
-    float4 v;
-    v.x = __ldg(in);
-    v.y = __ldg(in + HW);
-    v.z = __ldg(in + 2 * HW);
-    v.w = __ldg(in + 3 * HW);
-    reinterpret_cast<float4*>(src_c4)[i] = v;
-    (void)nch;
-    return;
-  }
-  i -= nt;
   const long long nc = cur_c4 ? (long long)s.B * (s.C / 4) * HW : 0;
-  if (i < nc) {
-    // same layout for the reference-frame features: (B,C/4,H,W,4)
-    const long long bj = i / HW, p = i - bj * HW;
-    const float* in = cur + bj * 4 * HW + p;
-    float4 v;
-    v.x = __ldg(in);
-    v.y = __ldg(in + HW);
-    v.z = __ldg(in + 2 * HW);
-    v.w = __ldg(in + 3 * HW);
-    reinterpret_cast<float4*>(cur_c4)[i] = v;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // NCHW -> chunk-planar (B,K,C/4,H,W,4) for the sources and (B,C/4,H,W,4) for the reference
+  // features.  A thread transposes a 4-pixel x 4-channel block: four 16-byte reads (one per
+  // channel plane, coalesced across the warp) and four 16-byte writes (64 contiguous bytes);
+  // needs H*W % 4 == 0 for the vector reads, otherwise one pixel per thread.
+  const bool vec4 = (HW & 3) == 0;
+  const long long ppt = vec4 ? 4 : 1;                      // pixels per thread
+  const long long nt_thr = nt / ppt, nc_thr = nc / ppt;
+  if (i < nt_thr + nc_thr) {
+    const bool is_cur = i >= nt_thr;
+    const long long e = (is_cur ? i - nt_thr : i) * ppt;   // first (chunk, pixel) element index
+    const long long cj = e / HW, p = e - cj * HW;          // cj = (image * C/4 + chunk)
+    const float* in = (is_cur ? cur : src) + cj * 4 * HW + p;
+    float4* out = reinterpret_cast<float4*>(is_cur ? cur_c4 : src_c4) + e;
+    if (vec4) {
+      const float4 c0 = __ldg(reinterpret_cast<const float4*>(in));
+      const float4 c1 = __ldg(reinterpret_cast<const float4*>(in + HW));
+      const float4 c2 = __ldg(reinterpret_cast<const float4*>(in + 2 * HW));
+      const float4 c3 = __ldg(reinterpret_cast<const float4*>(in + 3 * HW));
+      out[0] = make_float4(c0.x, c1.x, c2.x, c3.x);
+      out[1] = make_float4(c0.y, c1.y, c2.y, c3.y);
+      out[2] = make_float4(c0.z, c1.z, c2.z, c3.z);
+      out[3] = make_float4(c0.w, c1.w, c2.w, c3.w);
+    } else {
+      out[0] = make_float4(__ldg(in), __ldg(in + HW), __ldg(in + 2 * HW), __ldg(in + 3 * HW));
+    }
     return;
   }
-  i -= nc;
+  i -= nt_thr + nc_thr;
+  if (i < n_done) { tile_done[i] = 0u; return; }
+  i -= n_done;
   if (i < nv) {
     const long long b = i / s.K;
     view_params(cams.src_Ks + i * 16, cams.src_extrinsics + i * 16, cams.cur_invK + b * 16,
@@ -177,10 +179,12 @@ Workspace carve_workspace(const srcv_shape& s, void* base, bool want_c4, size_t 
     ws.src_c4 = reinterpret_cast<float*>(
         take(sizeof(float) * (size_t)s.B * s.K * s.C * s.H * s.W));
     ws.cur_c4 = reinterpret_cast<float*>(take(sizeof(float) * (size_t)s.B * s.C * s.H * s.W));
+    ws.tile_done_count = dot_fast_tile_counters(s);
+    ws.tile_done = reinterpret_cast<unsigned*>(take(sizeof(unsigned) * ws.tile_done_count));
   }
   if (extra_bytes) ws.extra = reinterpret_cast<float*>(take(extra_bytes));
   ws.bytes = off;
-  if (!p) { ws.planes = nullptr; ws.views = nullptr; ws.frames = nullptr; ws.src_c4 = nullptr; ws.cur_c4 = nullptr; ws.extra = nullptr; }
+  if (!p) { ws.planes = nullptr; ws.views = nullptr; ws.frames = nullptr; ws.src_c4 = nullptr; ws.cur_c4 = nullptr; ws.tile_done = nullptr; ws.extra = nullptr; }
   return ws;
 }
 
@@ -193,12 +197,14 @@ cudaError_t launch_prep(const srcv_shape& s, const srcv_cameras& cams, const src
   const long long np = (pl.mode == SRCV_PLANES_FROM_RANGE) ? (long long)s.B * s.D : 0;
   const long long nt = ws.src_c4 ? nv * (s.C / 4) * s.H * s.W : 0;
   const long long ncur = (ws.src_c4 && ws.cur_c4) ? (long long)s.B * (s.C / 4) * s.H * s.W : 0;
-  const long long total = nt + ncur + nv + s.B + np;
+  const long long ppt = (((long long)s.H * s.W) & 3) == 0 ? 4 : 1;
+  const long long ndone = ws.tile_done ? (long long)ws.tile_done_count : 0;
+  const long long total = nt / ppt + ncur / ppt + ndone + nv + s.B + np;
   const int threads = 256;
   const long long blocks = (total + threads - 1) / threads;
   prep_kernel<<<(unsigned)blocks, threads, 0, stream>>>(s, c, pl, src_feats, cur_feats, ws.planes,
                                                         ws.views, ws.frames, ws.src_c4,
-                                                        ncur ? ws.cur_c4 : nullptr);
+                                                        ncur ? ws.cur_c4 : nullptr, ws.tile_done, ndone);
   note_launch();
   return cudaGetLastError();
 }

@@ -54,6 +54,15 @@ CONFIGS = [
 ]
 
 
+# Stress shape of SURVEY.md §8: the FEATURE MAP itself is 480x640 (16x the pixels of the
+# BASELINE configs; 137 MB of source features per frame, larger than L2).  Not a BASELINE
+# config — `bench.py --workload stress_dot` / `stress_hero` report it for context.
+STRESS = [
+    Workload("stress_dot_480x640map_D64_K7_B1", "dot", 1, 7, 480, 640, 64),
+    Workload("stress_hero_480x640map_D64_K7_B1", "mlp", 1, 7, 480, 640, 64),
+]
+
+
 def matching_intrinsics(height: int, width: int) -> torch.Tensor:
     """4x4 K at the matching resolution for a (4*height)x(4*width) frame of a
     640x480 ScanNet-like camera."""

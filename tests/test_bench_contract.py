@@ -1,0 +1,32 @@
+"""CPU: the reference arm of bench.py runs here (it is the CPU port) and prints the contract's
+JSON line; the GPU arm's helpers are importable."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_reference_arm_prints_contract_line():
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--workload", "cfg0",
+                        "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
+              "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert line["config"]["workload"].startswith("cfg0")
+
+
+def test_algorithmic_bytes_match_survey():
+    sys.path.insert(0, str(ROOT))
+    import bench
+    from simplerecon_b200.synthetic import CONFIGS
+    # cfgA 14.82 MB (dot) / 14.84 MB (hero) per frame
+    assert abs(bench.algorithmic_bytes_per_frame(CONFIGS[1], False, True) - 14.82e6) < 0.02e6
+    assert abs(bench.algorithmic_bytes_per_frame(CONFIGS[2], True, True) - 14.84e6) < 0.02e6
+    assert abs(bench.algorithmic_bytes_per_frame(CONFIGS[3], True, True) - 17.30e6) < 0.03e6

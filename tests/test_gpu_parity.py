@@ -291,3 +291,24 @@ def test_host_streamer_matches_direct_calls():
         for b, out in zip(batches, got):
             cost, lowest, _, _ = m(**to_device(b, "cuda"))
             assert torch.equal(out[0], cost.cpu()) and torch.equal(out[1], lowest.cpu())
+
+
+def test_hero_cfg3_planes_96_and_batch_shards():
+    """BASELINE configs[3]: hero, D = 96, sharded 4 frames per GPU — one shard here, checked for
+    shard invariance and against the oracle on a plane subset (caller-supplied planes)."""
+    w = CONFIGS[3]
+    t = make_workload_tuple(w, batch=4)
+    sd = mlp_state(7, 16, seed=0)
+    (cost, lowest, planes, mask), used = run_gpu("mlp", t, w.planes, sd)
+    assert "tc" in used and cost.shape == (4, 96, 120, 160)
+    t1 = {k: (v[3:] if v.dim() > 0 and v.shape[0] == 4 else v) for k, v in t.items()}
+    (cost1, lowest1, _, mask1), _ = run_gpu("mlp", t1, w.planes, sd)
+    assert torch.equal(cost1, cost[3:]) and torch.equal(lowest1, lowest[3:]) and torch.equal(mask1, mask[3:])
+    # oracle on planes 90..95 of frame 3 via explicit per-plane depths
+    sub = planes[3:, 90:].cpu().contiguous()
+    wts = O.mlp_weights_from_state_dict(sd)
+    oc, ol, op, om = O.forward_mlp(**t1, weights=wts, num_depth_bins=6, depth_planes_bdhw=sub, return_mask=True)
+    oc64, *_ = O.forward_mlp(**{k: v.double() for k, v in t1.items()}, weights=tuple(x.double() for x in wts),
+                             num_depth_bins=6, depth_planes_bdhw=sub.double())
+    assert_cost_close("mlp", cost[3:, 90:], oc, oc64, what="cfg3 planes 90-95")
+    assert_mask_close(mask[3:], om)
