@@ -298,13 +298,15 @@ def main():
     l2_note = (f"{n_sets} rotating input sets, {n_sets * in_bytes / 2**20:.0f} MiB > 126 MiB L2; "
                f"outputs ({4 * per_gpu * w.planes * w.height * w.width / 2**20:.0f} MiB/step) freshly allocated")
 
-    if hero:
-        mgr = S.FeatureVolumeManager(w.height, w.width, num_depth_bins=w.planes,
-                                     mlp_channels=[0, 128, 128, 1], matching_dim_size=w.channels,
-                                     num_source_views=w.views)
-        mgr.load_state_dict({**mgr.state_dict(), **mlp_state(w.views, w.channels)})
-    else:
-        mgr = S.CostVolumeManager(w.height, w.width, num_depth_bins=w.planes)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):   # the managers print a banner like the reference's;
+        if hero:                                   # stdout carries the ONE JSON line only
+            mgr = S.FeatureVolumeManager(w.height, w.width, num_depth_bins=w.planes,
+                                         mlp_channels=[0, 128, 128, 1], matching_dim_size=w.channels,
+                                         num_source_views=w.views)
+            mgr.load_state_dict({**mgr.state_dict(), **mlp_state(w.views, w.channels)})
+        else:
+            mgr = S.CostVolumeManager(w.height, w.width, num_depth_bins=w.planes)
     mgr = mgr.to(dev).eval()
     kw = dict(return_mask=True) if hero else {}
 
