@@ -312,3 +312,31 @@ def test_hero_cfg3_planes_96_and_batch_shards():
                              num_depth_bins=6, depth_planes_bdhw=sub.double())
     assert_cost_close("mlp", cost[3:, 90:], oc, oc64, what="cfg3 planes 90-95")
     assert_mask_close(mask[3:], om)
+
+
+def test_bench_gpu_arm_prints_one_json_line():
+    """bench.py (ours, N=1, default workload): stdout is exactly ONE JSON line with the contract's
+    keys, kernels were launched, and the roofline / e2e / clock blocks are populated."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--steps", "10", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e",
+              "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["steps"] == 10 and d["value"] > 0 and d["gpu_launches"] >= 20
+    assert d["config"]["workload"].startswith("cfg1") and d["dtype"] == "f32" and d["scaling"] == "weak"
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and 0 < rf["frac"] < 1.5 and rf["peak"] > 1000 and rf["achieved"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] > 3.9e7 and d["e2e"]["d2h_bytes_per_step"] > 1.9e7
+    assert 0 < d["e2e"]["value"] <= d["value"] * 1.05
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    assert d["clocks"]["sm_max_mhz"] and not (set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"})
