@@ -13,7 +13,12 @@ from simplerecon_b200 import _native  # noqa: E402
 from simplerecon_b200.synthetic import CONFIGS, make_workload_tuple, mlp_state, to_device  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg1"
+import dataclasses  # noqa: E402
+import os  # noqa: E402
+
 w = next(c for c in CONFIGS if c.name.startswith(name))
+if os.environ.get("SRCV_SMALL"):          # sanitizer runs: same kernels, 37x53 map, 5 planes
+    w = dataclasses.replace(w, height=37, width=53, planes=5)
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else w.batch
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 variant = sys.argv[4] if len(sys.argv) > 4 else "auto"
