@@ -362,12 +362,9 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
   const int tiles_x = (W + kTileW - 1) / kTileW, tiles_xy = tiles_x * ((H + kTileH - 1) / kTileH);
 
   // ---- one-time setup ----------------------------------------------------------------
-  {
-    const uint4* g = reinterpret_cast<const uint4*>(image);
-    uint4* sdst = reinterpret_cast<uint4*>(smem);
-    for (uint32_t i = tid; i < kImageBytes / 16; i += kThreads) sdst[i] = __ldg(g + i);
-  }
+  uint64_t* bar_img = bars + 6;       // weight image landed in shared memory (bulk copies)
   if (tid == 0) {
+    mbar_init(bar_img, 1);
     mbar_init(bar_a1_full, kWorkers);
     mbar_init(bar_mma1, 1);
     mbar_init(bar_a2_full, kWorkers);
@@ -377,10 +374,19 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
     mbar_fence_init();
   }
   if (warp == kMmaWarp) tmem_alloc(&s_tmem_base, kTmemCols);
-  fence_proxy_async_smem();   // weight image: generic-proxy stores -> tensor-core reads
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
+  // The 170 KB weight image (fp16 core matrices + biases) is pulled in by the bulk-copy
+  // (TMA) engine straight into shared memory — written by the async proxy, which is also
+  // the proxy the tensor core reads it through — while the threads finish their setup.
+  if (tid == 0) {
+    mbar_expect_tx(bar_img, kImageBytes);
+    constexpr uint32_t kPiece = 32768;
+    for (uint32_t off = 0; off < kImageBytes; off += kPiece)
+      bulk_g2s(smem + off, image + off, (kImageBytes - off < kPiece) ? (kImageBytes - off) : kPiece, bar_img);
+  }
+  mbar_wait(bar_img, 0);
   const uint32_t tmem_base = s_tmem_base;
   const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   // Work split: CTA c takes tiles c, c + grid, c + 2 grid, ... of the plane-fastest tile
