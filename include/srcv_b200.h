@@ -123,6 +123,19 @@ int32_t srcv_dot_forward_f32(const srcv_shape* shape,
                              void* workspace, size_t workspace_bytes,
                              void* stream);
 
+/* ---- backward of the dot-product volume (training) ----------------------- *
+ * Gradients of a scalar loss w.r.t. the FEATURE inputs of srcv_dot_forward_f32, given
+ * grad_cost = dL/dcost (B,D,H,W) — what autograd of the reference's composite
+ * (modules/cost_volume.py:305-333: grid_sample, mul, sum) yields for cur_feats and
+ * src_feats.  Cameras and plane depths get no gradient.  C must be 8, 16 or 32.
+ *   grad_cur (B,C,H,W) out      grad_src (B,K,C,H,W) out (zeroed here, then accumulated
+ *   with float atomics: reproducible to fp32 rounding, not bit-for-bit)           */
+size_t srcv_dot_backward_workspace_bytes(const srcv_shape* shape);
+int32_t srcv_dot_backward_f32(const srcv_shape* shape, const float* cur_feats, const float* src_feats,
+                              const srcv_cameras* cams, const srcv_planes* planes,
+                              const float* grad_cost, float* grad_cur, float* grad_src,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- single-plane warp -------------------------------------------------- *
  * Replaces CostVolumeManager.warp_features (reference modules/cost_volume.py:139-234),
  * the helper that MATERIALISES the warped source features of one depth plane; the

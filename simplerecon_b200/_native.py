@@ -57,6 +57,9 @@ SYMBOLS = {
     "srcv_dot_workspace_bytes": (C.c_size_t, [C.POINTER(Shape)]),
     "srcv_dot_forward_f32": (C.c_int32, [C.POINTER(Shape), _fp, _fp, C.POINTER(Cameras),
                                          C.POINTER(Planes), _fp, _fp, _fp, C.c_size_t, _fp]),
+    "srcv_dot_backward_workspace_bytes": (C.c_size_t, [C.POINTER(Shape)]),
+    "srcv_dot_backward_f32": (C.c_int32, [C.POINTER(Shape), _fp, _fp, C.POINTER(Cameras), C.POINTER(Planes),
+                                          _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
     "srcv_warp_workspace_bytes": (C.c_size_t, [C.POINTER(Shape)]),
     "srcv_warp_features_f32": (C.c_int32, [C.POINTER(Shape), _fp, C.POINTER(Cameras), _fp, C.c_int32,
                                            _fp, _fp, _fp, _fp, C.c_size_t, _fp]),

@@ -40,6 +40,55 @@ def _f32c(t: Tensor, name: str, device) -> Tensor:
     return t
 
 
+class _DotVolumeFunction(torch.autograd.Function):
+    """Differentiable wrapper of the dot-product sweep: fused forward, and a backward kernel
+    (``srcv_dot_backward_f32``) for the two feature inputs — what autograd of the reference's
+    grid_sample / mul / sum composite (modules/cost_volume.py:305-333) yields for them.
+    Cameras and plane depths get no gradient.  fp16 / bf16 features (autocast) are upcast."""
+
+    @staticmethod
+    def forward(ctx, mgr, cur_feats, src_feats, src_extrinsics, src_Ks, cur_invK, min_depth, max_depth,
+                depth_planes_bdhw):
+        cur32, src32 = cur_feats.float(), src_feats.float()
+        cost, lowest, planes_ret, _ = mgr._run_fused(
+            cur32, src32, src_extrinsics.float(), None, src_Ks.float(), cur_invK.float(), min_depth,
+            max_depth, depth_planes_bdhw, True, allow_grad=True)
+        B, D, H, W = cost.shape
+        st = planes_ret.stride()
+        per_pixel = not ((st[2] == 0 or H == 1) and (st[3] == 0 or W == 1))
+        planes = planes_ret[:, :D].contiguous() if per_pixel else planes_ret[:, :D, 0, 0].contiguous()
+        ctx.save_for_backward(cur32, src32, src_extrinsics.float(), src_Ks.float(), cur_invK.float(), planes)
+        ctx.per_pixel = per_pixel
+        ctx.in_dtypes = (cur_feats.dtype, src_feats.dtype)
+        ctx.mark_non_differentiable(lowest, planes_ret)
+        return cost, lowest, planes_ret
+
+    @staticmethod
+    def backward(ctx, grad_cost, _grad_lowest, _grad_planes):
+        cur, src, E, Ks, invK, planes = ctx.saved_tensors
+        lib = _native.load()
+        dev = cur.device
+        B, K, Cc, H, W = src.shape
+        D = grad_cost.shape[1]
+        shape = _native.Shape(B, K, Cc, H, W, D)
+        cams = _native.Cameras(E.contiguous().data_ptr(), None, Ks.contiguous().data_ptr(),
+                               invK.contiguous().data_ptr())
+        pl = _native.Planes()
+        pl.mode = _native.PLANES_PER_PIXEL if ctx.per_pixel else _native.PLANES_PER_PLANE
+        pl.planes = planes.data_ptr()
+        pl.min_depth = pl.max_depth = pl.ramp = pl.planes_out = None
+        g = grad_cost.float().contiguous()
+        with torch.cuda.device(dev):
+            gcur = torch.empty_like(cur)
+            gsrc = torch.empty_like(src)
+            n = lib.srcv_dot_backward_workspace_bytes(C.byref(shape))
+            ws = torch.empty(n, device=dev, dtype=torch.uint8)
+            _native.check(lib.srcv_dot_backward_f32(
+                C.byref(shape), _ptr(cur), _ptr(src), C.byref(cams), C.byref(pl), _ptr(g), _ptr(gcur),
+                _ptr(gsrc), _ptr(ws), n, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        return (None, gcur.to(ctx.in_dtypes[0]), gsrc.to(ctx.in_dtypes[1]), None, None, None, None, None, None)
+
+
 class CostVolumeManager(nn.Module):
     """Dot-product plane-sweep cost volume (reference modules/cost_volume.py:13-380).
 
@@ -117,7 +166,7 @@ class CostVolumeManager(nn.Module):
     # shared argument handling
     # ------------------------------------------------------------------------
     def _prepare(self, cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK,
-                 min_depth, max_depth, depth_planes_bdhw, need_poses):
+                 min_depth, max_depth, depth_planes_bdhw, need_poses, allow_grad=False):
         if not torch.is_tensor(src_feats) or src_feats.dim() != 5:
             raise ValueError("src_feats must be a (B,K,C,H,W) tensor")
         dev = src_feats.device
@@ -125,13 +174,14 @@ class CostVolumeManager(nn.Module):
             raise RuntimeError(
                 "simplerecon_b200 cost volumes run on CUDA (sm_100a) only; got tensors on "
                 f"{dev}.  There is no CPU fallback.")
-        if torch.is_grad_enabled() and (
+        if not allow_grad and torch.is_grad_enabled() and (
                 cur_feats.requires_grad or src_feats.requires_grad
                 or any(p.requires_grad for p in self.parameters())
         ):
             raise NotImplementedError(
-                "the fused cost volume is forward-only; call it under torch.no_grad() / "
-                "torch.inference_mode() (the fused backward is the next scope row, SURVEY.md §8f-1)")
+                "the fused metadata-MLP volume is forward-only; call it under torch.no_grad() / "
+                "torch.inference_mode() (its fused backward is a next scope row, SURVEY.md §8f-1; "
+                "the dot-product CostVolumeManager is differentiable)")
         B, K, Cc, H, W = src_feats.shape
         if (H, W) != (self.matching_height, self.matching_width):
             raise ValueError(f"feature map {H}x{W} does not match the manager's "
@@ -208,10 +258,21 @@ class CostVolumeManager(nn.Module):
     def _run(self, cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK, min_depth,
              max_depth, depth_planes_bdhw, return_mask, want_lowest):
         # `src_poses` and `return_mask` are ignored by the dot-product volume (:286)
+        if torch.is_grad_enabled() and (cur_feats.requires_grad or src_feats.requires_grad):
+            # training: same fused forward, gradients w.r.t. the features by the backward kernel
+            cost, lowest, planes_ret = _DotVolumeFunction.apply(
+                self, cur_feats, src_feats, src_extrinsics, src_Ks, cur_invK, min_depth, max_depth,
+                depth_planes_bdhw)
+            return cost, (lowest if want_lowest else None), planes_ret, None
+        return self._run_fused(cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK,
+                               min_depth, max_depth, depth_planes_bdhw, want_lowest)
+
+    def _run_fused(self, cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK, min_depth,
+                   max_depth, depth_planes_bdhw, want_lowest, allow_grad=False):
         lib = _native.load()
         dev, shape, t, cams, pl, planes_ret, keep = self._prepare(
             cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK, min_depth,
-            max_depth, depth_planes_bdhw, need_poses=False)
+            max_depth, depth_planes_bdhw, need_poses=False, allow_grad=allow_grad)
         with torch.cuda.device(dev):
             cost = torch.empty(shape.B, shape.D, shape.H, shape.W, device=dev, dtype=torch.float32)
             lowest = torch.empty(shape.B, shape.H, shape.W, device=dev, dtype=torch.float32) \

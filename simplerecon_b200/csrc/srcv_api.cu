@@ -176,6 +176,35 @@ int32_t srcv_dot_forward_f32(const srcv_shape* s, const float* cur, const float*
   return SRCV_OK;
 }
 
+size_t srcv_dot_backward_workspace_bytes(const srcv_shape* s) {
+  if (check_shape(s) != SRCV_OK) return 0;
+  return carve_workspace(*s, nullptr, false, 0).bytes;
+}
+
+int32_t srcv_dot_backward_f32(const srcv_shape* s, const float* cur, const float* src,
+                              const srcv_cameras* cams, const srcv_planes* pl, const float* grad_cost,
+                              float* grad_cur, float* grad_src, void* workspace,
+                              size_t workspace_bytes, void* stream_) {
+  if (int32_t e = check_common(s, cur, src, cams, pl, grad_cost, false)) return e;
+  if (!grad_cur || !grad_src) return fail(SRCV_ERR_NULL, "grad_cur / grad_src is NULL");
+  if (!dot_backward_supported(*s))
+    return fail(SRCV_ERR_UNSUPPORTED, "dot backward is built for C in {8, 16, 32}, got %d", s->C);
+  const Workspace need = carve_workspace(*s, nullptr, false, 0);
+  if (int32_t e = check_workspace(workspace, workspace_bytes, need.bytes)) return e;
+  Workspace ws = carve_workspace(*s, workspace, false, 0);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  cudaError_t err = launch_prep(*s, *cams, *pl, src, cur, ws, false, stream);
+  if (err != cudaSuccess) return cuda_fail(err, "prep");
+  err = cudaMemsetAsync(grad_src, 0, sizeof(float) * (size_t)s->B * s->K * s->C * s->H * s->W, stream);
+  if (err != cudaSuccess) return cuda_fail(err, "memset grad_src");
+  const bool per_pixel = pl->mode == SRCV_PLANES_PER_PIXEL;
+  const float* planes = pl->mode == SRCV_PLANES_FROM_RANGE ? ws.planes : pl->planes;
+  g_last_variant = "dot_backward_atomic";
+  err = launch_dot_backward(*s, cur, src, ws, planes, per_pixel, grad_cost, grad_cur, grad_src, stream);
+  if (err != cudaSuccess) return cuda_fail(err, g_last_variant);
+  return SRCV_OK;
+}
+
 size_t srcv_warp_workspace_bytes(const srcv_shape* s) {
   if (check_shape(s) != SRCV_OK) return 0;
   return carve_workspace(*s, nullptr, false, 0).bytes;

@@ -42,6 +42,12 @@ cudaError_t launch_dot_fast(const srcv_shape& s, const float* cur, const Workspa
                             const float* planes, bool per_pixel, float* cost, float* lowest,
                             cudaStream_t stream);
 
+// backward of the dot-product volume w.r.t. the feature inputs
+bool dot_backward_supported(const srcv_shape& s);
+cudaError_t launch_dot_backward(const srcv_shape& s, const float* cur, const float* src,
+                                const Workspace& ws, const float* planes, bool per_pixel,
+                                const float* gcost, float* gcur, float* gsrc, cudaStream_t stream);
+
 // single-plane warp (the reference's warp_features helper)
 cudaError_t launch_warp_plane(const srcv_shape& s, const float* src, const Workspace& ws,
                               const float* plane, bool per_pixel, float* warped, float* depths,

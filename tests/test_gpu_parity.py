@@ -237,13 +237,14 @@ def test_errors_on_device():
         bad = dict(t); bad["src_Ks"] = t["src_Ks"][:, :1]
         with pytest.raises(ValueError):
             m(**bad)
-    need = dict(t); need["cur_feats"] = t["cur_feats"].clone().requires_grad_(True)
-    with pytest.raises(NotImplementedError):
-        m(**need)
     # MLP input width inconsistent with K, C
     f = S.FeatureVolumeManager(12, 16, 4, matching_dim_size=16, num_source_views=7).cuda()
     with torch.no_grad(), pytest.raises(ValueError):
         f(**t)
+    # the metadata-MLP volume is forward-only (its parameters require grad): loud, not silent
+    f2 = S.FeatureVolumeManager(12, 16, 4, matching_dim_size=16, num_source_views=2).cuda()
+    with pytest.raises(NotImplementedError):
+        f2(**t)
     _native.set_variant(_native.VARIANT_FAST)
     t8 = to_device(make_tuple(1, 2, 12, 16, channels=8, seed=33), "cuda")
     with torch.no_grad(), pytest.raises(_native.SrcvError):
@@ -340,3 +341,42 @@ def test_bench_gpu_arm_prints_one_json_line():
     assert 0 < d["e2e"]["value"] <= d["value"] * 1.05
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
     assert d["clocks"]["sm_max_mhz"] and not (set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"})
+
+
+@pytest.mark.parametrize("B,K,C,H,W,D,seed,per_pixel", [
+    (2, 3, 16, 14, 18, 5, 71, False),
+    (1, 7, 16, 24, 32, 8, 72, False),
+    (1, 2, 8, 10, 12, 4, 73, True),
+])
+def test_dot_backward_matches_autograd_of_the_oracle(B, K, C, H, W, D, seed, per_pixel):
+    """Training path of CostVolumeManager: dL/dcur_feats and dL/dsrc_feats from the backward
+    kernel against CPU autograd through the oracle (the composite the reference differentiates,
+    modules/cost_volume.py:305-333)."""
+    t = make_tuple(B, K, H, W, channels=C, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    gcost = torch.randn(B, D, H, W, generator=g)
+    planes = (0.3 + 4.0 * torch.rand(B, D, H, W, generator=g)) if per_pixel else None
+    # oracle + autograd (CPU)
+    tc = dict(t)
+    tc["cur_feats"] = t["cur_feats"].clone().requires_grad_(True)
+    tc["src_feats"] = t["src_feats"].clone().requires_grad_(True)
+    oc, *_ = O.forward_dot(**tc, num_depth_bins=D, depth_planes_bdhw=planes)
+    (oc * gcost).sum().backward()
+    # fused forward + backward kernel (GPU)
+    d = to_device(t, "cuda")
+    d["cur_feats"] = d["cur_feats"].clone().requires_grad_(True)
+    d["src_feats"] = d["src_feats"].clone().requires_grad_(True)
+    m = make_manager("dot", K, C, H, W, D)
+    cost, lowest, planes_ret, mask = m(**d, depth_planes_bdhw=planes.cuda() if per_pixel else None)
+    assert cost.requires_grad and not lowest.requires_grad and mask is None
+    assert_cost_close("dot", cost, oc.detach())
+    (cost * gcost.cuda()).sum().backward()
+    assert _native.last_variant() == "dot_backward_atomic"
+    for name in ("cur_feats", "src_feats"):
+        ours, ref = d[name].grad.cpu(), tc[name].grad
+        tol = 5e-5 * float(ref.abs().max()) + 1e-6
+        assert (ours - ref).abs().max().item() <= tol, name
+    # inference calls on the same manager still take the plain fused path
+    with torch.no_grad():
+        c2, *_ = m(**{k: v.detach() for k, v in d.items()}, depth_planes_bdhw=planes.cuda() if per_pixel else None)
+    assert torch.equal(c2, cost.detach())

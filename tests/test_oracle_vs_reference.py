@@ -52,3 +52,25 @@ def test_pose_distance_matches_live_reference():
     rc, rr, rt = R.pose_distance(t["src_poses"].reshape(-1, 4, 4))
     assert torch.allclose(comb.reshape(-1), rc) and torch.allclose(r.reshape(-1), rr)
     assert torch.allclose(tm.reshape(-1), rt)
+
+
+def test_dot_gradients_match_live_reference_autograd():
+    """The oracle's autograd (which the GPU backward kernel is tested against) equals autograd
+    through the reference's own CostVolumeManager for the two feature inputs."""
+    R = load_reference()
+    B, K, H, W, D = 2, 3, 10, 14, 4
+    t = make_tuple(B, K, H, W, seed=17)
+    g = torch.randn(B, D, H, W, generator=torch.Generator().manual_seed(1))
+    grads = []
+    for impl in ("ref", "oracle"):
+        tt = dict(t)
+        tt["cur_feats"] = t["cur_feats"].clone().requires_grad_(True)
+        tt["src_feats"] = t["src_feats"].clone().requires_grad_(True)
+        if impl == "ref":
+            cost, *_ = R.CostVolumeManager(H, W, num_depth_bins=D)(**tt)
+        else:
+            cost, *_ = O.forward_dot(**tt, num_depth_bins=D, sampler="explicit")
+        (cost * g).sum().backward()
+        grads.append((tt["cur_feats"].grad, tt["src_feats"].grad))
+    for a, b in zip(*grads):
+        assert (a - b).abs().max().item() <= 2e-5 * float(a.abs().max()) + 1e-6
