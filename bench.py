@@ -352,7 +352,7 @@ def main():
         pin = [{k: v.pin_memory() for k, v in s_.items()} for s_ in sets_host[:3]]
         h2d = sum(v.numel() * v.element_size() for v in pin[0].values())
         streamer = HostStreamer(mgr, dev, return_mask=hero)
-        outs = list(streamer.run(pin[i % 3] for i in range(4)))          # warm-up
+        outs = list(streamer.run(pin[i % len(pin)] for i in range(4)))   # warm-up
         d2h = sum(t.numel() * t.element_size() for t in outs[-1])
         e2e_steps = max(5, min(args.steps, 50))
         sharding.barrier()
@@ -361,7 +361,7 @@ def main():
         t_wall0 = time.perf_counter()
         e0.record()
         n_out = 0
-        for host_res in streamer.run(pin[i % 3] for i in range(e2e_steps)):
+        for host_res in streamer.run(pin[i % len(pin)] for i in range(e2e_steps)):
             n_out += 1
         e1.record()
         torch.cuda.synchronize()
@@ -408,6 +408,29 @@ def main():
         "clocks": clocks,
         "kernel_variant": variant,
     }
+    if rank == 0 and world == 1:
+        # second comparator: the reference's PyTorch composite (the oracle port, i.e.
+        # its per-plane grid_sample / cat / Linear sequence) on THIS GPU — what a user of the
+        # reference gets today on the same hardware, library kernels only.
+        try:
+            from oracle import costvolume_oracle as O
+            frames_g = min(per_gpu, 2 if hero else 4)
+            tg = {k: v[:frames_g] if (torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == per_gpu) else v
+                  for k, v in sets_dev[0].items()}
+            wg = tuple(x.to(dev) for x in O.mlp_weights_from_state_dict(mlp_state(w.views, w.channels))) if hero else None
+            with torch.inference_mode():
+                cpu_port_step(w, tg, wg)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(2):
+                    cpu_port_step(w, tg, wg)
+                e1.record()
+                torch.cuda.synchronize()
+            line["torch_gpu_port"] = {
+                "value": 2 * frames_g / (e0.elapsed_time(e1) * 1e-3), "unit": UNIT,
+                "sample": f"{frames_g} frame(s), 2 reps, oracle port (reference op sequence) on cuda:{local}"}
+        except Exception as ex:  # pragma: no cover - informational only
+            line["torch_gpu_port"] = {"value": None, "error": str(ex)[:200]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         frames = 1 if hero else 2
         fps, cores, sample = time_cpu_port(w, frames, min_seconds=10.0, max_reps=5)

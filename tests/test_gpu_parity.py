@@ -380,3 +380,16 @@ def test_dot_backward_matches_autograd_of_the_oracle(B, K, C, H, W, D, seed, per
     with torch.no_grad():
         c2, *_ = m(**{k: v.detach() for k, v in d.items()}, depth_planes_bdhw=planes.cuda() if per_pixel else None)
     assert torch.equal(c2, cost.detach())
+
+
+def test_dot_large_batch_unsplit_plane_loop():
+    """B = 64 small frames: enough warps that the plane loop is NOT split, i.e. the argmax is
+    fused in the sweep itself (the other tests run the split, last-arriver form)."""
+    B, K, H, W, D = 64, 2, 60, 80, 8
+    t = make_tuple(B, K, H, W, seed=91)
+    (cost, lowest, planes, _), used = run_gpu("dot", t, D, variant="fast")
+    oc, ol, op, _ = O.forward_dot(**t, num_depth_bins=D)
+    assert_cost_close("dot", cost, oc, what="B=64")
+    assert_lowest_close("dot", lowest, planes, oc, what="B=64")
+    idx = cost.argmax(1, keepdim=True)
+    assert torch.equal(torch.gather(planes.expand_as(cost), 1, idx).squeeze(1), lowest)
