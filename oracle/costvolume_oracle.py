@@ -49,27 +49,27 @@ LRELU_SLOPE = 0.01    # nn.LeakyReLU() default, modules/networks.py:140
 # --------------------------------------------------------------------------- #
 # geometry                                                                    #
 # --------------------------------------------------------------------------- #
-def depth_planes(min_depth, max_depth, num_depth_bins: int, dtype=torch.float32):
+def depth_planes(min_depth, max_depth, num_depth_bins: int, dtype=torch.float32, device=None):
     """(D,) log-spaced plane depths.  modules/cost_volume.py:68-70, :124-127."""
-    min_depth = torch.as_tensor(min_depth, dtype=dtype).reshape(())
-    max_depth = torch.as_tensor(max_depth, dtype=dtype).reshape(())
+    min_depth = torch.as_tensor(min_depth, dtype=dtype, device=device).reshape(())
+    max_depth = torch.as_tensor(max_depth, dtype=dtype, device=device).reshape(())
     # the reference builds the ramp in fp32 (register_buffer) and then .double()
     # converts the buffer, so an fp64 run still sees the fp32-rounded ramp.
-    ramp = torch.linspace(0, 1, num_depth_bins).to(dtype)
+    ramp = torch.linspace(0, 1, num_depth_bins).to(dtype).to(min_depth.device)
     return torch.exp(torch.log(min_depth) + torch.log(max_depth / min_depth) * ramp)
 
 
-def pixel_centres(H: int, W: int, dtype=torch.float32):
+def pixel_centres(H: int, W: int, dtype=torch.float32, device=None):
     """(3, H*W) homogeneous pixel centres, xy order.  utils/geometry_utils.py:34-44."""
     v, u = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
     return torch.stack(
         [u.reshape(-1) + 0.5, v.reshape(-1) + 0.5, torch.ones(H * W)], 0
-    ).to(dtype)
+    ).to(dtype).to(device)
 
 
 def backproject_rays(cur_invK, H: int, W: int):
     """(B,3,N): r = invK[:3,:3] @ p.  utils/geometry_utils.py:56."""
-    return torch.matmul(cur_invK[:, :3, :3], pixel_centres(H, W, cur_invK.dtype)[None])
+    return torch.matmul(cur_invK[:, :3, :3], pixel_centres(H, W, cur_invK.dtype, cur_invK.device)[None])
 
 
 def project(points_b3n, src_Ks, src_extrinsics):
@@ -148,10 +148,10 @@ def bounds_mask(px, py, H: int, W: int):
     return (px > 2) & (px < W - 2) & (py > 2) & (py < H - 2)
 
 
-def _planes_bdn(depth_planes_bdhw, min_depth, max_depth, B, D, H, W, dtype):
+def _planes_bdn(depth_planes_bdhw, min_depth, max_depth, B, D, H, W, dtype, device=None):
     """Returns (planes (B,D,N) view-able tensor, depth_planes_bdhw to hand back)."""
     if depth_planes_bdhw is None:
-        d = depth_planes(min_depth, max_depth, D, dtype)
+        d = depth_planes(min_depth, max_depth, D, dtype, device)
         depth_planes_bdhw = d.view(1, D, 1, 1).expand(B, D, H, W)   # :129-134
     return depth_planes_bdhw.reshape(B, D, H * W), depth_planes_bdhw
 
@@ -166,7 +166,7 @@ def dot_volume(cur_feats, src_feats, src_extrinsics, src_Ks, cur_invK,
     B, K, C, H, W = src_feats.shape
     D = num_depth_bins if depth_planes_bdhw is None else depth_planes_bdhw.shape[1]
     planes, depth_planes_bdhw = _planes_bdn(depth_planes_bdhw, min_depth, max_depth,
-                                            B, D, H, W, cur_feats.dtype)
+                                            B, D, H, W, cur_feats.dtype, cur_feats.device)
     rays = backproject_rays(cur_invK, H, W)                        # (B,3,N)
     cur = cur_feats.reshape(B, 1, C, H * W)
     out = []
@@ -230,7 +230,7 @@ def feature_volume(cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_
     B, K, C, H, W = src_feats.shape
     D = num_depth_bins if depth_planes_bdhw is None else depth_planes_bdhw.shape[1]
     planes, depth_planes_bdhw = _planes_bdn(depth_planes_bdhw, min_depth, max_depth,
-                                            B, D, H, W, cur_feats.dtype)
+                                            B, D, H, W, cur_feats.dtype, cur_feats.device)
     out, overall = [], None
     for d in range(D):                                             # :557
         feat, px, py, zp = feature_rows(cur_feats, src_feats, src_extrinsics, src_poses,
