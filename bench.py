@@ -408,10 +408,11 @@ def main():
         "clocks": clocks,
         "kernel_variant": variant,
     }
-    if rank == 0 and world == 1:
-        # second comparator: the reference's PyTorch composite (the oracle port, i.e.
-        # its per-plane grid_sample / cat / Linear sequence) on THIS GPU — what a user of the
-        # reference gets today on the same hardware, library kernels only.
+    gpu_port = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # part of the baseline leg (SURVEY.md §8d "second comparator"): the same port — the
+        # reference's per-plane grid_sample / cat / Linear sequence — run on THIS GPU, i.e. what a
+        # user of the reference gets today on the same hardware from library kernels.
         try:
             from oracle import costvolume_oracle as O
             frames_g = min(per_gpu, 2 if hero else 4)
@@ -426,15 +427,16 @@ def main():
                     cpu_port_step(w, tg, wg)
                 e1.record()
                 torch.cuda.synchronize()
-            line["torch_gpu_port"] = {
+            gpu_port = {
                 "value": 2 * frames_g / (e0.elapsed_time(e1) * 1e-3), "unit": UNIT,
-                "sample": f"{frames_g} frame(s), 2 reps, oracle port (reference op sequence) on cuda:{local}"}
+                "sample": f"{frames_g} frame(s), 2 reps, the port's op sequence as PyTorch CUDA ops on cuda:{local}"}
         except Exception as ex:  # pragma: no cover - informational only
-            line["torch_gpu_port"] = {"value": None, "error": str(ex)[:200]}
+            gpu_port = {"value": None, "error": str(ex)[:200]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         frames = 1 if hero else 2
         fps, cores, sample = time_cpu_port(w, frames, min_seconds=10.0, max_reps=5)
-        line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                                "port_on_this_gpu": gpu_port}
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
