@@ -393,3 +393,43 @@ def test_dot_large_batch_unsplit_plane_loop():
     assert_lowest_close("dot", lowest, planes, oc, what="B=64")
     idx = cost.argmax(1, keepdim=True)
     assert torch.equal(torch.gather(planes.expand_as(cost), 1, idx).squeeze(1), lowest)
+
+
+def _edge_views(t):
+    """View 1 looks backwards (every plane point behind the camera: mask 0, features still
+    sampled), view 2 is shifted 40 m sideways (every sample outside the frustum)."""
+    E = t["src_extrinsics"].clone()
+    E[:, 1] = torch.tensor([[-1., 0, 0, 0.05], [0, 1, 0, 0], [0, 0, -1, -0.1], [0, 0, 0, 1]])
+    E[:, 2, :3, :3] = torch.eye(3)
+    E[:, 2, :3, 3] = torch.tensor([40.0, 0.0, 0.0])
+    t = dict(t)
+    t["src_extrinsics"] = E
+    t["src_poses"] = torch.linalg.inv(E.double()).float()
+    return t
+
+
+@pytest.mark.parametrize("variant", ["generic", "fast"])
+def test_hero_k7_edge_views_and_per_pixel_planes(variant):
+    """The tensor-core kernel (and the SIMT one) on the reference's corner cases at the hero
+    layout: behind-camera and out-of-frustum source views, caller-supplied per-pixel depth
+    hypotheses (including a non-positive one), partial tiles."""
+    B, K, H, W, D = 1, 7, 19, 27, 4
+    t = _edge_views(make_tuple(B, K, H, W, seed=81))
+    sd = mlp_state(K, 16, seed=5)
+    g = torch.Generator().manual_seed(82)
+    planes = 0.3 + 4.0 * torch.rand(B, D, H, W, generator=g)
+    planes[0, 1, 3, 4] = 0.0          # degenerate hypothesis: the point is the camera centre
+    planes[0, 2, 5, 6] = -1.0         # behind the reference camera
+    w = O.mlp_weights_from_state_dict(sd)
+    for dp in (None, planes):
+        kw = dict(t)
+        if dp is not None:
+            kw["depth_planes_bdhw"] = dp
+        (cost, lowest, pl, mask), used = run_gpu("mlp", kw, D, sd, variant)
+        assert ("tc" in used) == (variant == "fast")
+        oc, ol, op, om = O.forward_mlp(**t, weights=w, num_depth_bins=D, depth_planes_bdhw=dp, return_mask=True)
+        oc64, *_ = O.forward_mlp(**{k: v.double() for k, v in t.items()}, weights=tuple(x.double() for x in w),
+                                 num_depth_bins=D, depth_planes_bdhw=None if dp is None else dp.double())
+        assert torch.isfinite(cost).all()
+        assert_cost_close("mlp", cost, oc, oc64, what=f"edge {variant} per_pixel={dp is not None}")
+        assert_mask_close(mask, om, max_frac=5e-3)
