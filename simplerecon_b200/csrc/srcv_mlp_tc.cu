@@ -4,8 +4,8 @@
 // (reference modules/cost_volume.py:451-736, :967-1164) for the hero layout
 // K = 7 source views, C = 16 channels, MLP 202 -> 128 -> 128 -> 1.
 //
-// One persistent CTA per SM walks over row tiles; a tile = 128 rows = a 16 x 8 block of
-// pixels at one depth plane.  Sixteen "row worker" warps (four threads per row) and one
+// One persistent CTA per SM walks over row tiles; a tile = 128 rows = a 16 x 2 patch of
+// pixels at four consecutive depth planes.  Sixteen "row worker" warps (four threads per row) and one
 // MMA-issuing thread run this per-tile pipeline:
 //   1. the workers project, gather (chunk-planar copies of the features, csrc/srcv_prep.cu)
 //      and build the row's 202 metadata channels in registers, split every value into an
@@ -42,7 +42,10 @@ using namespace tc;
 
 constexpr int kC = 16, kViews = 7;
 constexpr int kRows = 128;               // rows (TMEM lanes) per tile
-constexpr int kTileW = 16, kTileH = 8;   // pixel block of a tile
+// A tile is a 16 x 2 pixel patch at FOUR consecutive depth planes (32 pixels x 4 planes =
+// 128 rows): warp w of a lane group works plane w of the same patch, so the four warps'
+// gathers for one source view walk along the same epipolar lines and share L1 lines.
+constexpr int kTileW = 16, kTileH = 2, kTileD = 4;
 constexpr int kN = 128;                  // layer widths
 constexpr int kBlk = kC + 10;            // channels per view block (26)
 constexpr int kK1 = 208;                 // 7*26 + 20 + 6 pad  (13 k-steps of 16)
@@ -262,12 +265,14 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_base, uint32_t col_hi,
   }
 }
 
-struct TileCoord { int b, d, x0, y0; };
+struct TileCoord { int b, d0, x0, y0; };
 
+// tile id runs plane-chunk fastest, then pixel patch, then frame
 __device__ __forceinline__ TileCoord tile_coord(long long id, int D, int tiles_x, int tiles_xy) {
   TileCoord t;
-  t.d = (int)(id % D);
-  const long long r = id / D;
+  const int nd = (D + kTileD - 1) / kTileD;
+  t.d0 = (int)(id % nd) * kTileD;
+  const long long r = id / nd;
   const int txy = (int)(r % tiles_xy);
   t.b = (int)(r / tiles_xy);
   t.x0 = (txy % tiles_x) * kTileW;
@@ -284,18 +289,21 @@ struct TileRow {
 };
 
 template <bool PER_PIXEL>
-__device__ __forceinline__ void make_tile_row(long long id, int rx, int ry, int W, int H, int HW, int D,
+__device__ __forceinline__ void make_tile_row(long long id, int row, int W, int H, int HW, int D,
                                               int tiles_x, int tiles_xy, const Centre& ctr,
                                               const FrameParams* __restrict__ frames,
                                               const float* __restrict__ planes, TileRow& tr) {
   const TileCoord t = tile_coord(id, D, tiles_x, tiles_xy);
-  tr.b = t.b; tr.d = t.d;
-  tr.active = (t.x0 + rx < W) && (t.y0 + ry < H);
+  // row -> (plane-in-chunk = row / 32, pixel of the 16 x 2 patch = row % 32)
+  const int rx = row & (kTileW - 1), ry = (row >> 4) & (kTileH - 1), dd = row >> 5;
+  tr.b = t.b;
+  tr.d = min(t.d0 + dd, D - 1);
+  tr.active = (t.x0 + rx < W) && (t.y0 + ry < H) && (t.d0 + dd < D);
   const int ox = min(t.x0 + rx, W - 1), oy = min(t.y0 + ry, H - 1);
   tr.p = oy * W + ox;
   const float pxc = (float)ox + 0.5f, pyc = (float)oy + 0.5f;
   RowCtx& rc = tr.rc;
-  rc.dval = PER_PIXEL ? __ldg(planes + ((size_t)t.b * D + t.d) * HW + tr.p) : __ldg(planes + t.b * D + t.d);
+  rc.dval = PER_PIXEL ? __ldg(planes + ((size_t)t.b * D + tr.d) * HW + tr.p) : __ldg(planes + t.b * D + tr.d);
   rc.dxc = pxc - ctr.half_w;
   rc.dyc = pyc - ctr.half_h;
   // rays: X = d * (invK3 p); n_cur = X / max(|X|, 1e-12)
@@ -401,7 +409,6 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
   if (warp < kWorkWarps) {
     // =============================== row workers =========================================
     const int row = tid & (kRows - 1), q = tid >> 7;
-    const int rx = row & (kTileW - 1), ry = row >> 4;
     const Centre ctr(W, H);
     const int blk0 = 2 * q, blk1 = 2 * q + 1;   // q = 3: view 6 and the tail block (7)
     TileRow cur_row, nxt_row;
@@ -409,7 +416,7 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
     long long id = tile_begin;
     if (id < tile_end) {
       // prologue: the first tile's A operand (its columns are free)
-      make_tile_row<PER_PIXEL>(tile_id(id), rx, ry, W, H, HW, D, tiles_x, tiles_xy, ctr, frames, planes, cur_row);
+      make_tile_row<PER_PIXEL>(tile_id(id), row, W, H, HW, D, tiles_x, tiles_xy, ctr, frames, planes, cur_row);
       unsigned bits = build_block<TW, HWC>(cur_row, blk0, cur4g, src4, views, W, H, HW, ctr, hi, lo);
       store_block(lane_base, (uint32_t)(13 * blk0), hi, lo);
       bits |= build_block<TW, HWC>(cur_row, blk1, cur4g, src4, views, W, H, HW, ctr, hi, lo);
@@ -426,7 +433,7 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
       unsigned nbits = 0;
       if (has_next) {
         // first K block of the NEXT tile, built while this tile's layer-1 MMAs run
-        make_tile_row<PER_PIXEL>(tile_id(nid), rx, ry, W, H, HW, D, tiles_x, tiles_xy, ctr, frames, planes, nxt_row);
+        make_tile_row<PER_PIXEL>(tile_id(nid), row, W, H, HW, D, tiles_x, tiles_xy, ctr, frames, planes, nxt_row);
         nbits = build_block<TW, HWC>(nxt_row, blk0, cur4g, src4, views, W, H, HW, ctr, hi, lo);
       }
       // ---- layer-1 epilogue on columns [32q, 32q+32): bias + LeakyReLU, (hi, lo), A2 -> TMEM
@@ -632,7 +639,7 @@ cudaError_t launch_mlp_tc(const srcv_shape& s, const float* cur, const Workspace
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles_x = (s.W + kTileW - 1) / kTileW, tiles_y = (s.H + kTileH - 1) / kTileH;
-  const long long num_tiles = (long long)s.B * s.D * tiles_x * tiles_y;
+  const long long num_tiles = (long long)s.B * ((s.D + kTileD - 1) / kTileD) * tiles_x * tiles_y;
   const int grid = (int)(num_tiles < sms ? num_tiles : sms);
   const float4* src4 = reinterpret_cast<const float4*>(ws.src_c4);
   const float4* cur4 = reinterpret_cast<const float4*>(ws.cur_c4);
