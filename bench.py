@@ -130,7 +130,8 @@ class ClockSampler:
             if not self.active.is_set():
                 time.sleep(0.0005)
                 continue
-            time.sleep(0.002)   # ~500 samples/s; a busy poll would fight the timed loop for the GIL
+            time.sleep(0.010)   # ~100 samples/s: NVML queries take driver locks that CUDA calls of the timed
+                                # loop also need, and a busy poll would fight it for the GIL
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:

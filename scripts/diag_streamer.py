@@ -54,10 +54,17 @@ ev.clear()
 base = torch.cuda.Event(enable_timing=True)
 base.record()
 t0 = time.perf_counter()
-n = 8
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 list(st.run(pin[i % 3] for i in range(n)))
 torch.cuda.synchronize()
 wall = time.perf_counter() - t0
 print(f"{name}: {n} steps wall {1e3 * wall:.2f} ms -> {1e3 * wall / n:.2f} ms/step")
-for kind, e0, e1, th in ev:
-    print(f"  {kind}: start {base.elapsed_time(e0):8.2f} ms  dur {e0.elapsed_time(e1):6.2f} ms   issued at host t={1e3 * (th - t0):7.2f} ms")
+d2h = [(base.elapsed_time(e0), e0.elapsed_time(e1)) for kind, e0, e1, th in ev if kind == "d2h"]
+h2d = [(base.elapsed_time(e0), e0.elapsed_time(e1)) for kind, e0, e1, th in ev if kind == "h2d"]
+if n <= 10:
+    for kind, e0, e1, th in ev:
+        print(f"  {kind}: start {base.elapsed_time(e0):8.2f} ms  dur {e0.elapsed_time(e1):6.2f} ms   issued at host t={1e3 * (th - t0):7.2f} ms")
+else:
+    for i in range(0, len(d2h) - 10, 10):
+        print(f"  steps {i:3d}-{i + 10:3d}: {(d2h[i + 10][0] - d2h[i][0]) / 10:.2f} ms/step between D2H starts; "
+              f"h2d dur {sum(x[1] for x in h2d[i:i + 10]) / 10:.2f} ms, d2h dur {sum(x[1] for x in d2h[i:i + 10]) / 10:.2f} ms")
