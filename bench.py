@@ -211,6 +211,31 @@ def time_cpu_port(w, frames: int, min_seconds: float, max_reps: int):
                                   f"{cores} of {os.cpu_count()} host threads (fastest of a probe)")
 
 
+def time_c_port(w, frames: int):
+    """The plain-C restatement (oracle/cv_oracle.c, OpenMP over pixels, all host threads): a CPU
+    number that scales with the core count where the ATen-op port does not."""
+    try:
+        from oracle import c_oracle as CO
+        from oracle import costvolume_oracle as O
+        from simplerecon_b200.synthetic import make_workload_tuple, mlp_state
+        tup = make_workload_tuple(w, batch=frames)
+        if w.kind == "dot":
+            fn = lambda: CO.forward_dot(**tup, num_depth_bins=w.planes)
+        else:
+            wts = O.mlp_weights_from_state_dict(mlp_state(w.views, w.channels))
+            fn = lambda: CO.forward_mlp(**tup, weights=wts, num_depth_bins=w.planes, return_mask=True)
+        fn()
+        best = float("inf")
+        for _ in range(2):
+            t0 = time.perf_counter()
+            fn()
+            best = min(best, time.perf_counter() - t0)
+        return {"value": frames / best, "unit": UNIT, "threads": os.cpu_count(),
+                "sample": f"{frames} frame(s), best of 2, fp32 scalar loops + OpenMP"}
+    except Exception as ex:  # pragma: no cover - informational only
+        return {"value": None, "error": str(ex)[:200]}
+
+
 def run_reference_arm(args, w):
     """`--impl reference`: the reference's CPU implementation (port) of the same
     workload, all host threads, rank 0 only."""
@@ -437,7 +462,7 @@ def main():
         frames = 1 if hero else 2
         fps, cores, sample = time_cpu_port(w, frames, min_seconds=10.0, max_reps=5)
         line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                                "port_on_this_gpu": gpu_port}
+                                "port_on_this_gpu": gpu_port, "c_port_openmp": time_c_port(w, frames)}
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
