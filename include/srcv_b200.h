@@ -176,7 +176,7 @@ int32_t srcv_mlp_forward_f32(const srcv_shape* shape,
 typedef enum srcv_variant {
   SRCV_VARIANT_AUTO = 0,
   SRCV_VARIANT_GENERIC = 1, /* shape-generic SIMT kernels                     */
-  SRCV_VARIANT_FAST = 2     /* channel-last gather / tensor-core kernels      */
+  SRCV_VARIANT_FAST = 2     /* chunk-planar gather / tcgen05 kernels          */
 } srcv_variant;
 int32_t srcv_set_variant(int32_t variant);
 /* Name of the kernel variant the last forward call on this process launched. */

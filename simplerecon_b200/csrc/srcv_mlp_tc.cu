@@ -28,7 +28,7 @@
 // The K order of layer 1 is OURS (the pack kernel permutes W1's columns to match):
 //   per view k (26 channels): 16 warped | mask | z' | dot | ray angle | n_src (3) | comb | r | t
 //   tail (20 + 6 pad):        16 reference features | plane depth | n_cur (3) | zeros
-// i.e. every producer thread writes 2 x 26 = 52 consecutive K positions; the first of its
+// i.e. every worker thread writes 2 x 26 = 52 consecutive K positions; the first of its
 // two blocks is computed before it waits for the A columns to be free, so producing tile
 // t+1 overlaps the layer-1 MMAs of tile t.
 #include "srcv_kernels.h"
@@ -190,7 +190,7 @@ __device__ __forceinline__ unsigned view_block(const RowCtx& rc, const ViewParam
   const float4* q = view4 + (tp.y0 * W + tp.x0);
   // features are sampled even for points behind the camera (only the dot is masked,
   // reference modules/cost_volume.py:590-623); padding taps contribute zeros
-  // two taps (8 vector loads) in flight at a time keeps the producer inside its register budget
+  // two taps (8 vector loads) in flight at a time keeps the worker inside its register budget
   const bool interior = __all_sync(0xffffffffu, tp.valid == 15u);
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
