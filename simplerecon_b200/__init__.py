@@ -11,6 +11,7 @@ from .cost_volume import CostVolumeManager, FastFeatureVolumeManager, FeatureVol
 from .geometry import BackprojectDepth, Project3D, pose_distance
 from .install import install, uninstall
 from .networks import MLP
+from . import torch_ops  # noqa: E402,F401  registers torch.ops.b200cv.{dot_forward,dot_backward,mlp_forward}
 
 __all__ = [
     "CostVolumeManager", "FeatureVolumeManager", "FastFeatureVolumeManager", "MLP",
