@@ -168,6 +168,30 @@ int32_t srcv_mlp_forward_f32(const srcv_shape* shape,
                              void* workspace, size_t workspace_bytes,
                              void* stream);
 
+/* ---- metadata-MLP volume, backward ------------------------------------ *
+ * What autograd of the reference composite (modules/cost_volume.py:451-736 with the
+ * MLP of modules/networks.py:129-147; used for training by
+ * experiment_modules/depth_model.py:362-372 under train.py) yields for the two feature
+ * inputs and the six MLP parameters, given dL/dcost.  Nothing of the forward is saved:
+ * the kernel recomputes the metadata tile and the activations per 64-row tile.  Every
+ * output is OVERWRITTEN (zeroed, then accumulated with fp32 atomics — the summation
+ * order, hence the last bits, may differ between calls).  Cameras and plane depths get
+ * no gradient.  Supported: C (K+1) + 10 K + 4 <= 208 features, hidden widths <= 128.
+ *   grad_cost (B,D,H,W)   grad_cur (B,C,H,W)   grad_src (B,K,C,H,W)
+ *   grads     DEVICE pointers shaped like the parameters in srcv_mlp_weights        */
+typedef struct srcv_mlp_grads {
+  float* w1; float* b1;
+  float* w2; float* b2;
+  float* w3; float* b3;
+} srcv_mlp_grads;
+size_t srcv_mlp_backward_workspace_bytes(const srcv_shape* shape, const srcv_mlp_weights* w);
+int32_t srcv_mlp_backward_f32(const srcv_shape* shape,
+                              const float* cur_feats, const float* src_feats,
+                              const srcv_cameras* cams, const srcv_planes* planes,
+                              const srcv_mlp_weights* weights, const float* grad_cost,
+                              float* grad_cur, float* grad_src, const srcv_mlp_grads* grads,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- tuning / introspection ------------------------------------------- *
  * Selects the kernel variant used by the two forward calls on this thread's
  * next invocations (process-global).  0 = automatic choice.  Used by the tests

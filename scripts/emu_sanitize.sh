@@ -1,0 +1,27 @@
+#!/usr/bin/env bash
+# Runs tests/test_emu_kernels.py (the SIMT kernels compiled for the host, tests/emu) under
+# ThreadSanitizer — a missing __syncthreads() shows up as a data race on the emulated shared
+# memory — and AddressSanitizer — out-of-bounds global / shared accesses.  CPU only.
+#   scripts/emu_sanitize.sh [thread|address ...]   (default: both)   report -> stdout
+set -u
+cd "$(dirname "$0")/.."
+CXX=/usr/bin/g++
+for san in "${@:-thread address}"; do
+  for s in $san; do
+    lib=$(python -c "from tests import emu; print(emu.build(sanitize='$s'))") || exit 1
+    case $s in
+      thread)  rt=$($CXX -print-file-name=libtsan.so); opts="TSAN_OPTIONS=halt_on_error=0:report_signal_unsafe=0" ;;
+      address) rt=$($CXX -print-file-name=libasan.so); opts="ASAN_OPTIONS=detect_leaks=0" ;;
+      *) echo "unknown sanitizer $s"; exit 2 ;;
+    esac
+    echo "== $s sanitizer: $lib"
+    log=$(mktemp)
+    env LD_PRELOAD="$rt" $opts SRCV_EMU_LIB="$lib" python -m pytest tests/test_emu_kernels.py -q -x -p no:cacheprovider >"$log" 2>&1
+    rc=$?
+    tail -n 3 "$log"
+    echo "pytest exit code: $rc"
+    echo "sanitizer reports: $(grep -c -E 'WARNING: ThreadSanitizer|ERROR: AddressSanitizer' "$log")"
+    grep -E 'SUMMARY: (Thread|Address)Sanitizer' "$log" | sort | uniq -c | head -20
+    rm -f "$log"
+  done
+done

@@ -48,6 +48,10 @@ class MlpWeights(C.Structure):
                 ("hidden1", C.c_int32), ("hidden2", C.c_int32)]
 
 
+class MlpGrads(C.Structure):
+    _fields_ = [(n, _fp) for n in ("w1", "b1", "w2", "b2", "w3", "b3")]
+
+
 # every symbol include/srcv_b200.h declares: (restype, argtypes)
 SYMBOLS = {
     "srcv_abi_version": (C.c_int32, []),
@@ -67,6 +71,10 @@ SYMBOLS = {
     "srcv_mlp_forward_f32": (C.c_int32, [C.POINTER(Shape), _fp, _fp, C.POINTER(Cameras),
                                          C.POINTER(Planes), C.POINTER(MlpWeights), _fp, _fp, _fp,
                                          _fp, C.c_size_t, _fp]),
+    "srcv_mlp_backward_workspace_bytes": (C.c_size_t, [C.POINTER(Shape), C.POINTER(MlpWeights)]),
+    "srcv_mlp_backward_f32": (C.c_int32, [C.POINTER(Shape), _fp, _fp, C.POINTER(Cameras), C.POINTER(Planes),
+                                          C.POINTER(MlpWeights), _fp, _fp, _fp, C.POINTER(MlpGrads), _fp,
+                                          C.c_size_t, _fp]),
     "srcv_set_variant": (C.c_int32, [C.c_int32]),
     "srcv_last_variant": (C.c_char_p, []),
     "srcv_launch_count": (C.c_uint64, []),

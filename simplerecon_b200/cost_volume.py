@@ -23,6 +23,16 @@ from .geometry import BackprojectDepth, Project3D
 from .networks import MLP
 
 
+def _require_cuda(dev) -> None:
+    """The one device gate of the managers: CUDA tensors only, no CPU / PyTorch fallback.
+    (tests/test_emu_python_stack.py patches exactly this to drive the Python layer against the
+    host-emulated library; the product never bypasses it.)"""
+    if dev.type != "cuda":
+        raise RuntimeError(
+            "simplerecon_b200 cost volumes run on CUDA (sm_100a) only; got tensors on "
+            f"{dev}.  There is no CPU fallback.")
+
+
 def _ptr(t: Tensor | None):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -89,6 +99,67 @@ class _DotVolumeFunction(torch.autograd.Function):
         return (None, gcur.to(ctx.in_dtypes[0]), gsrc.to(ctx.in_dtypes[1]), None, None, None, None, None, None)
 
 
+class _MlpVolumeFunction(torch.autograd.Function):
+    """Differentiable wrapper of the metadata-MLP sweep: fused forward (tcgen05 where the
+    shape allows), and ``srcv_mlp_backward_f32`` — a recompute kernel, nothing but the inputs
+    is saved — for the two feature inputs and the six MLP parameters: what autograd of the
+    reference composite (modules/cost_volume.py:451-736, modules/networks.py:129-147) yields.
+    Cameras and plane depths get no gradient.  fp16 / bf16 features (autocast) are upcast."""
+
+    @staticmethod
+    def forward(ctx, mgr, return_mask, cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK,
+                min_depth, max_depth, depth_planes_bdhw, w1, b1, w2, b2, w3, b3):
+        cur32, src32 = cur_feats.float(), src_feats.float()
+        cams = [t.float() for t in (src_extrinsics, src_poses, src_Ks, cur_invK)]
+        cost, lowest, planes_ret, mask = mgr._run_fused(
+            cur32, src32, cams[0], cams[1], cams[2], cams[3], min_depth, max_depth, depth_planes_bdhw,
+            return_mask, True, allow_grad=True)
+        B, D, H, W = cost.shape
+        st = planes_ret.stride()
+        per_pixel = not ((st[2] == 0 or H == 1) and (st[3] == 0 or W == 1))
+        planes = planes_ret[:, :D].contiguous() if per_pixel else planes_ret[:, :D, 0, 0].contiguous()
+        ctx.save_for_backward(cur32, src32, *cams, planes, w1, b1, w2, b2, w3, b3)
+        ctx.per_pixel = per_pixel
+        ctx.in_dtypes = (cur_feats.dtype, src_feats.dtype)
+        if mask is None:
+            mask = torch.empty(0, dtype=torch.bool, device=cost.device)
+        ctx.mark_non_differentiable(lowest, planes_ret, mask)
+        return cost, lowest, planes_ret, mask
+
+    @staticmethod
+    def backward(ctx, grad_cost, _gl, _gp, _gm):
+        cur, src, E, P, Ks, invK, planes, *wts = ctx.saved_tensors
+        lib = _native.load()
+        dev = cur.device
+        B, K, Cc, H, W = src.shape
+        D = grad_cost.shape[1]
+        shape = _native.Shape(B, K, Cc, H, W, D)
+        keep = [t.contiguous() for t in (E, P, Ks, invK)]
+        cams = _native.Cameras(*[t.data_ptr() for t in keep])
+        pl = _native.Planes()
+        pl.mode = _native.PLANES_PER_PIXEL if ctx.per_pixel else _native.PLANES_PER_PLANE
+        pl.planes = planes.data_ptr()
+        pl.min_depth = pl.max_depth = pl.ramp = pl.planes_out = None
+        wc = [_f32c(t.detach(), "mlp parameter", dev) for t in wts]
+        w = _native.MlpWeights(*[t.data_ptr() for t in wc], wc[0].shape[0], wc[2].shape[0])
+        g = grad_cost.float().contiguous()
+        with torch.cuda.device(dev):
+            gcur, gsrc = torch.empty_like(cur), torch.empty_like(src)
+            gw = [torch.empty_like(t) for t in wc]
+            grads = _native.MlpGrads(*[t.data_ptr() for t in gw])
+            n = lib.srcv_mlp_backward_workspace_bytes(C.byref(shape), C.byref(w))
+            if n == 0:
+                raise NotImplementedError("metadata-MLP backward: at most 208 input features, hidden widths <= 128")
+            ws = torch.empty(n, device=dev, dtype=torch.uint8)
+            _native.check(lib.srcv_mlp_backward_f32(
+                C.byref(shape), _ptr(cur), _ptr(src), C.byref(cams), C.byref(pl), C.byref(w), _ptr(g),
+                _ptr(gcur), _ptr(gsrc), C.byref(grads), _ptr(ws), n,
+                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        gw = [a.to(b.dtype) for a, b in zip(gw, wts)]
+        return (None, None, gcur.to(ctx.in_dtypes[0]), gsrc.to(ctx.in_dtypes[1]), None, None, None, None,
+                None, None, None, *gw)
+
+
 class CostVolumeManager(nn.Module):
     """Dot-product plane-sweep cost volume (reference modules/cost_volume.py:13-380).
 
@@ -132,8 +203,7 @@ class CostVolumeManager(nn.Module):
         pixel coordinates)."""
         lib = _native.load()
         dev = src_feats.device
-        if dev.type != "cuda":
-            raise RuntimeError("simplerecon_b200 runs on CUDA (sm_100a) only; there is no CPU fallback.")
+        _require_cuda(dev)
         B, K, Cc = batch_size, num_src_frames, num_feat_channels
         H, W = self.matching_height, self.matching_width
         src = _f32c(src_feats, "src_feats", dev).reshape(B, K, Cc, H, W)
@@ -170,18 +240,12 @@ class CostVolumeManager(nn.Module):
         if not torch.is_tensor(src_feats) or src_feats.dim() != 5:
             raise ValueError("src_feats must be a (B,K,C,H,W) tensor")
         dev = src_feats.device
-        if dev.type != "cuda":
-            raise RuntimeError(
-                "simplerecon_b200 cost volumes run on CUDA (sm_100a) only; got tensors on "
-                f"{dev}.  There is no CPU fallback.")
+        _require_cuda(dev)
         if not allow_grad and torch.is_grad_enabled() and (
                 cur_feats.requires_grad or src_feats.requires_grad
                 or any(p.requires_grad for p in self.parameters())
         ):
-            raise NotImplementedError(
-                "the fused metadata-MLP volume is forward-only; call it under torch.no_grad() / "
-                "torch.inference_mode() (its fused backward is a next scope row, SURVEY.md §8f-1; "
-                "the dot-product CostVolumeManager is differentiable)")
+            raise RuntimeError("internal: a gradient-requiring call reached the plain fused path")
         B, K, Cc, H, W = src_feats.shape
         if (H, W) != (self.matching_height, self.matching_width):
             raise ValueError(f"feature map {H}x{W} does not match the manager's "
@@ -337,10 +401,27 @@ class FeatureVolumeManager(CostVolumeManager):
 
     def _run(self, cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK, min_depth,
              max_depth, depth_planes_bdhw, return_mask, want_lowest):
+        if torch.is_grad_enabled() and (cur_feats.requires_grad or src_feats.requires_grad
+                                        or any(p.requires_grad for p in self.mlp.parameters())):
+            # training: same fused forward; gradients for features and MLP parameters by the
+            # recompute backward kernel (srcv_mlp_backward_f32)
+            lin = [m for m in self.mlp.net if isinstance(m, nn.Linear)]
+            if len(lin) != 3 or any(l.bias is None for l in lin):
+                raise NotImplementedError("the fused kernels implement the reference's three-layer MLP with biases")
+            cost, lowest, planes_ret, mask = _MlpVolumeFunction.apply(
+                self, bool(return_mask), cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK,
+                min_depth, max_depth, depth_planes_bdhw, lin[0].weight, lin[0].bias, lin[1].weight,
+                lin[1].bias, lin[2].weight, lin[2].bias)
+            return cost, (lowest if want_lowest else None), planes_ret, (mask if return_mask else None)
+        return self._run_fused(cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK, min_depth,
+                               max_depth, depth_planes_bdhw, return_mask, want_lowest)
+
+    def _run_fused(self, cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK, min_depth,
+                   max_depth, depth_planes_bdhw, return_mask, want_lowest, allow_grad=False):
         lib = _native.load()
         dev, shape, t, cams, pl, planes_ret, keep = self._prepare(
             cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK, min_depth,
-            max_depth, depth_planes_bdhw, need_poses=True)
+            max_depth, depth_planes_bdhw, need_poses=True, allow_grad=allow_grad)
         n_features = shape.C * (shape.K + 1) + 10 * shape.K + 4
         w, wkeep = self._mlp_weights(dev, n_features)
         with torch.cuda.device(dev):

@@ -298,6 +298,50 @@ int32_t srcv_mlp_forward_f32(const srcv_shape* s, const float* cur, const float*
   return SRCV_OK;
 }
 
+size_t srcv_mlp_backward_workspace_bytes(const srcv_shape* s, const srcv_mlp_weights* w) {
+  if (check_shape(s) != SRCV_OK || !w) return 0;
+  if (!mlp_backward_supported(*s, *w)) return 0;
+  return carve_workspace(*s, nullptr, false, mlp_backward_extra_bytes(*s, *w)).bytes;
+}
+
+int32_t srcv_mlp_backward_f32(const srcv_shape* s, const float* cur, const float* src,
+                              const srcv_cameras* cams, const srcv_planes* pl,
+                              const srcv_mlp_weights* w, const float* grad_cost, float* grad_cur,
+                              float* grad_src, const srcv_mlp_grads* g, void* workspace,
+                              size_t workspace_bytes, void* stream_) {
+  if (int32_t e = check_common(s, cur, src, cams, pl, grad_cost, true)) return e;
+  if (int32_t e = check_weights(s, w)) return e;
+  if (!grad_cur || !grad_src) return fail(SRCV_ERR_NULL, "grad_cur / grad_src is NULL");
+  if (!g || !g->w1 || !g->b1 || !g->w2 || !g->b2 || !g->w3 || !g->b3)
+    return fail(SRCV_ERR_NULL, "a parameter-gradient pointer is NULL");
+  if (!mlp_backward_supported(*s, *w))
+    return fail(SRCV_ERR_UNSUPPORTED, "MLP backward supports at most 208 input features and hidden widths <= 128");
+  const size_t extra = mlp_backward_extra_bytes(*s, *w);
+  const Workspace need = carve_workspace(*s, nullptr, false, extra);
+  if (int32_t e = check_workspace(workspace, workspace_bytes, need.bytes)) return e;
+  Workspace ws = carve_workspace(*s, workspace, false, extra);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  cudaError_t err = launch_prep(*s, *cams, *pl, src, cur, ws, true, stream);
+  if (err != cudaSuccess) return cuda_fail(err, "prep");
+  const size_t F = (size_t)s->C * (s->K + 1) + 10 * (size_t)s->K + 4;
+  const size_t HW = (size_t)s->H * s->W;
+  struct { void* p; size_t n; } zero[] = {
+      {grad_cur, (size_t)s->B * s->C * HW}, {grad_src, (size_t)s->B * s->K * s->C * HW},
+      {g->w1, (size_t)w->hidden1 * F}, {g->b1, (size_t)w->hidden1},
+      {g->w2, (size_t)w->hidden2 * w->hidden1}, {g->b2, (size_t)w->hidden2},
+      {g->w3, (size_t)w->hidden2}, {g->b3, 1}};
+  for (auto& z : zero) {
+    err = cudaMemsetAsync(z.p, 0, sizeof(float) * z.n, stream);
+    if (err != cudaSuccess) return cuda_fail(err, "memset gradients");
+  }
+  const bool per_pixel = pl->mode == SRCV_PLANES_PER_PIXEL;
+  const float* planes = pl->mode == SRCV_PLANES_FROM_RANGE ? ws.planes : pl->planes;
+  g_last_variant = "mlp_backward_fp32_recompute";
+  err = launch_mlp_backward(*s, cur, src, ws, planes, per_pixel, *w, grad_cost, grad_cur, grad_src, *g, stream);
+  if (err != cudaSuccess) return cuda_fail(err, g_last_variant);
+  return SRCV_OK;
+}
+
 int32_t srcv_tc_selftest_f32(const float* A, const float* Wm, int32_t Kp, float* D, void* scratch,
                              void* stream) {
   if (!A || !Wm || !D || !scratch) return fail(SRCV_ERR_NULL, "selftest pointer is NULL");

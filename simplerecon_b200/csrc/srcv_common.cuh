@@ -22,8 +22,21 @@
 // fp64 evaluation of the reference this is closer than the reference's own fp32
 // result ("numerics").
 #pragma once
+#ifdef SRCV_HOST_EMU
+#include "emu_cuda.h"   // tests/emu: host emulation of the CUDA execution model
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
+
+// Dynamic shared memory of a kernel (one definition so the host emulation can map it).
+#ifdef SRCV_HOST_EMU
+#define SRCV_DYNAMIC_SMEM(type, name) type* name = reinterpret_cast<type*>(::emu::dynamic_smem())
+#define SRCV_DYNAMIC_SMEM_ALIGNED(type, name, n) SRCV_DYNAMIC_SMEM(type, name)
+#else
+#define SRCV_DYNAMIC_SMEM(type, name) extern __shared__ type name[]
+#define SRCV_DYNAMIC_SMEM_ALIGNED(type, name, n) extern __shared__ __align__(n) type name[]
+#endif
 
 namespace srcv {
 
@@ -82,7 +95,11 @@ __device__ __forceinline__ void project_point(float d, float ax, float ay, float
   // IEEE-rounded division's slow path; the residual is far below the pixel-coordinate
   // rounding that follows.
   float r;
+#ifdef SRCV_HOST_EMU
+  r = 1.0f / zp;
+#else
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(zp));
+#endif
   r = fmaf(r, fmaf(-zp, r, 1.0f), r);
   const float s = (fabsf(z) > kEpsProj) ? r : 1.0f;
   px = cx * s;
@@ -127,7 +144,11 @@ __device__ __forceinline__ float leaky(float x) { return fmaxf(x, kLeaky * x); }
 // division and no IEEE-sqrt slow path.  Used for F.normalize / cosine_similarity.
 __device__ __forceinline__ float inv_norm(float s, float eps) {
   float y;
+#ifdef SRCV_HOST_EMU
+  y = 1.0f / sqrtf(s);
+#else
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(s));
+#endif
   y = y * fmaf(-0.5f * s, y * y, 1.5f);
   return (s > eps * eps) ? y : __frcp_rn(eps);
 }

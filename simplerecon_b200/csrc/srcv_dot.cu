@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(128)
 dot_generic_kernel(srcv_shape s, const float* __restrict__ cur, const float* __restrict__ src,
                    const ViewParams* __restrict__ views, const float* __restrict__ planes,
                    float* __restrict__ cost, float* __restrict__ lowest) {
-  extern __shared__ float sview[];  // K * 12: a0, hx, hy, t
+  SRCV_DYNAMIC_SMEM(float, sview);  // K * 12: a0, hx, hy, t
   const int b = blockIdx.y;
   const int HW = s.H * s.W;
   for (int i = threadIdx.x; i < s.K * kViewFloats; i += blockDim.x)
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kFastWarps * 32)
 dot_fast_kernel(srcv_shape s, const float* __restrict__ cur, const float4* __restrict__ src4,
                 const ViewParams* __restrict__ views, const float* __restrict__ planes,
                 float* __restrict__ cost, float* __restrict__ lowest, unsigned* __restrict__ tile_done) {
-  extern __shared__ float sview[];  // K * 12
+  SRCV_DYNAMIC_SMEM(float, sview);  // K * 12
   const int b = blockIdx.y;
   const int W = TW ? TW : s.W, H = TH ? TH : s.H, HW = W * H, K = s.K;
   constexpr int HWC = TW * TH;
@@ -236,16 +236,16 @@ void launch_fast_sized(const srcv_shape& s, dim3 grid, dim3 block, size_t smem, 
                        const float* planes, float* cost, float* lowest, unsigned* tile_done) {
 #define SRCV_SIZED(TW_, TH_)                                                                   \
   if (s.W == TW_ && s.H == TH_) {                                                              \
-    dot_fast_kernel<PER_PIXEL, TW_, TH_, kTileW><<<grid, block, smem, stream>>>(                 \
-        s, cur, src4, views, planes, cost, lowest, tile_done);                                 \
+    SRCV_LAUNCH((dot_fast_kernel<PER_PIXEL, TW_, TH_, kTileW>), grid, block, smem, stream,       \
+                s, cur, src4, views, planes, cost, lowest, tile_done);                         \
     return;                                                                                    \
   }
   SRCV_SIZED(160, 120)  // 640x480 frames (BASELINE configs)
   SRCV_SIZED(128, 96)   // 512x384 frames (the reference's default, options.py:70-71)
   SRCV_SIZED(64, 48)    // 256x192 frames (BASELINE config 0)
 #undef SRCV_SIZED
-  dot_fast_kernel<PER_PIXEL, 0, 0, kTileW><<<grid, block, smem, stream>>>(s, cur, src4, views, planes, cost,
-                                                                          lowest, tile_done);
+  SRCV_LAUNCH((dot_fast_kernel<PER_PIXEL, 0, 0, kTileW>), grid, block, smem, stream, s, cur, src4, views, planes,
+              cost, lowest, tile_done);
 }
 
 // --------------------------------------------------------------------------- //
@@ -291,8 +291,8 @@ cudaError_t launch_warp_plane(const srcv_shape& s, const float* src, const Works
                               const float* plane, bool per_pixel, float* warped, float* depths,
                               float* mask, cudaStream_t stream) {
   dim3 grid((s.H * s.W + 127) / 128, s.B * s.K), block(128);
-  if (per_pixel) warp_plane_kernel<true><<<grid, block, 0, stream>>>(s, src, ws.views, plane, warped, depths, mask);
-  else warp_plane_kernel<false><<<grid, block, 0, stream>>>(s, src, ws.views, plane, warped, depths, mask);
+  if (per_pixel) SRCV_LAUNCH(warp_plane_kernel<true>, grid, block, 0, stream, s, src, ws.views, plane, warped, depths, mask);
+  else SRCV_LAUNCH(warp_plane_kernel<false>, grid, block, 0, stream, s, src, ws.views, plane, warped, depths, mask);
   note_launch();
   return cudaGetLastError();
 }
@@ -304,9 +304,9 @@ cudaError_t launch_dot_generic(const srcv_shape& s, const float* cur, const floa
   dim3 grid((HW + 127) / 128, s.B), block(128);
   const size_t smem = sizeof(float) * kViewFloats * s.K;
   if (per_pixel)
-    dot_generic_kernel<true><<<grid, block, smem, stream>>>(s, cur, src, ws.views, planes, cost, lowest);
+    SRCV_LAUNCH(dot_generic_kernel<true>, grid, block, smem, stream, s, cur, src, ws.views, planes, cost, lowest);
   else
-    dot_generic_kernel<false><<<grid, block, smem, stream>>>(s, cur, src, ws.views, planes, cost, lowest);
+    SRCV_LAUNCH(dot_generic_kernel<false>, grid, block, smem, stream, s, cur, src, ws.views, planes, cost, lowest);
   note_launch();
   return cudaGetLastError();
 }

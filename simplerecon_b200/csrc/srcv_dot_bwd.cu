@@ -26,7 +26,7 @@ dot_backward_kernel(srcv_shape s, const float* __restrict__ cur, const float* __
                     const ViewParams* __restrict__ views, const float* __restrict__ planes,
                     const float* __restrict__ gcost, float* __restrict__ gcur, float* __restrict__ gsrc,
                     int d_begin, int d_end, bool accumulate_gcur) {
-  extern __shared__ float sview[];  // K * 12
+  SRCV_DYNAMIC_SMEM(float, sview);  // K * 12
   const int b = blockIdx.y;
   const int W = s.W, H = s.H, HW = W * H, K = s.K;
   for (int i = threadIdx.x; i < K * kViewFloats; i += blockDim.x)
@@ -93,11 +93,11 @@ cudaError_t launch_dot_backward(const srcv_shape& s, const float* cur, const flo
 #define SRCV_BWD(CC)                                                                                  \
   if (s.C == CC) {                                                                                    \
     if (per_pixel)                                                                                    \
-      dot_backward_kernel<CC, true><<<grid, block, smem, stream>>>(s, cur, src, ws.views, planes, gcost, \
-                                                                  gcur, gsrc, 0, s.D, false);         \
+      SRCV_LAUNCH((dot_backward_kernel<CC, true>), grid, block, smem, stream, s, cur, src, ws.views,     \
+                  planes, gcost, gcur, gsrc, 0, s.D, false);                                          \
     else                                                                                              \
-      dot_backward_kernel<CC, false><<<grid, block, smem, stream>>>(s, cur, src, ws.views, planes, gcost, \
-                                                                   gcur, gsrc, 0, s.D, false);        \
+      SRCV_LAUNCH((dot_backward_kernel<CC, false>), grid, block, smem, stream, s, cur, src, ws.views,    \
+                  planes, gcost, gcur, gsrc, 0, s.D, false);                                          \
     note_launch();                                                                                    \
     return cudaGetLastError();                                                                        \
   }

@@ -1,11 +1,24 @@
 // Internal host-side launch interface between srcv_api.cu and the kernel files.
 #pragma once
+#ifdef SRCV_HOST_EMU
+#include "emu_cuda.h"   // tests/emu: the kernels compiled as host C++ (one std::thread per CUDA thread)
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stddef.h>
 #include <stdint.h>
 
 #include "../../include/srcv_b200.h"
 #include "srcv_common.cuh"
+
+// One spelling for a kernel launch, so that the host emulation (tests/emu) can run the same
+// launcher code: a template kernel name with commas goes in parentheses.
+#ifdef SRCV_HOST_EMU
+#define SRCV_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  ::emu::launch(dim3(grid), dim3(block), (size_t)(smem), [&] { kernel(__VA_ARGS__); })
+#else
+#define SRCV_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
 
 namespace srcv {
 
@@ -60,6 +73,14 @@ cudaError_t launch_mlp_generic(const srcv_shape& s, const float* cur, const floa
                                const Workspace& ws, const float* planes, bool per_pixel,
                                const srcv_mlp_weights& w, float* cost, float* lowest,
                                uint8_t* mask, cudaStream_t stream);
+
+// backward of the metadata-MLP volume (fp32 SIMT, recompute)
+bool mlp_backward_supported(const srcv_shape& s, const srcv_mlp_weights& w);
+size_t mlp_backward_extra_bytes(const srcv_shape& s, const srcv_mlp_weights& w);
+cudaError_t launch_mlp_backward(const srcv_shape& s, const float* cur, const float* src,
+                                const Workspace& ws, const float* planes, bool per_pixel,
+                                const srcv_mlp_weights& w, const float* gcost, float* gcur,
+                                float* gsrc, const srcv_mlp_grads& g, cudaStream_t stream);
 
 // tensor-core variant (tcgen05): K = 7, C = 16, 202 -> 128 -> 128 -> 1
 bool mlp_tc_supported(const srcv_shape& s, const srcv_mlp_weights& w);

@@ -105,7 +105,7 @@ mlp_generic_kernel(srcv_shape s, MlpDims m, const float* __restrict__ cur,
                    const float* __restrict__ w2t, const float* __restrict__ b2,
                    const float* __restrict__ w3, const float* __restrict__ b3,
                    float* __restrict__ cost, uint8_t* __restrict__ mask_out) {
-  extern __shared__ __align__(16) float smem[];
+  SRCV_DYNAMIC_SMEM_ALIGNED(float, smem, 16);
   float* sA = smem;                         // [rows][TM]
   float* sW = sA + (size_t)m.rows * TM;     // [2][KC][NMAX]  (also the 16 x TM partial buffer)
   int* sFlag = reinterpret_cast<int*>(sW + 2 * KC * NMAX);  // [TM] mask bits
@@ -273,7 +273,7 @@ cudaError_t launch_mlp_generic(const srcv_shape& s, const float* cur, const floa
   const MlpDims m = make_dims(s.K, s.C, w.hidden1, w.hidden2);
   float* w1t = ws.extra;
   float* w2t = ws.extra + (size_t)m.Fp * NMAX;
-  mlp_pack_weights_kernel<<<64, 256, 0, stream>>>(w.w1, w.w2, m, w1t, w2t);
+  SRCV_LAUNCH(mlp_pack_weights_kernel, 64, 256, 0, stream, w.w1, w.w2, m, w1t, w2t);
   note_launch();
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return err;
@@ -283,13 +283,13 @@ cudaError_t launch_mlp_generic(const srcv_shape& s, const float* cur, const floa
   if (per_pixel) {
     err = cudaFuncSetAttribute(mlp_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    mlp_generic_kernel<true><<<grid, block, smem, stream>>>(s, m, cur, src, ws.views, ws.frames, planes,
-                                                            w1t, w.b1, w2t, w.b2, w.w3, w.b3, cost, mask);
+    SRCV_LAUNCH(mlp_generic_kernel<true>, grid, block, smem, stream, s, m, cur, src, ws.views, ws.frames, planes,
+                w1t, w.b1, w2t, w.b2, w.w3, w.b3, cost, mask);
   } else {
     err = cudaFuncSetAttribute(mlp_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    mlp_generic_kernel<false><<<grid, block, smem, stream>>>(s, m, cur, src, ws.views, ws.frames, planes,
-                                                             w1t, w.b1, w2t, w.b2, w.w3, w.b3, cost, mask);
+    SRCV_LAUNCH(mlp_generic_kernel<false>, grid, block, smem, stream, s, m, cur, src, ws.views, ws.frames, planes,
+                w1t, w.b1, w2t, w.b2, w.w3, w.b3, cost, mask);
   }
   note_launch();
   err = cudaGetLastError();

@@ -202,9 +202,8 @@ cudaError_t launch_prep(const srcv_shape& s, const srcv_cameras& cams, const src
   const long long total = nt / ppt + ncur / ppt + ndone + nv + s.B + np;
   const int threads = 256;
   const long long blocks = (total + threads - 1) / threads;
-  prep_kernel<<<(unsigned)blocks, threads, 0, stream>>>(s, c, pl, src_feats, cur_feats, ws.planes,
-                                                        ws.views, ws.frames, ws.src_c4,
-                                                        ncur ? ws.cur_c4 : nullptr, ws.tile_done, ndone);
+  SRCV_LAUNCH(prep_kernel, (unsigned)blocks, threads, 0, stream, s, c, pl, src_feats, cur_feats, ws.planes,
+              ws.views, ws.frames, ws.src_c4, ncur ? ws.cur_c4 : nullptr, ws.tile_done, ndone);
   note_launch();
   return cudaGetLastError();
 }
@@ -214,10 +213,9 @@ cudaError_t launch_argmax(const srcv_shape& s, const float* cost, const float* p
   const long long n = (long long)s.B * s.H * s.W;
   const int threads = 256;
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);
-  if (per_pixel) argmax_kernel<true><<<blocks, threads, 0, stream>>>(s, cost, planes, lowest);
-  else argmax_kernel<false><<<blocks, threads, 0, stream>>>(s, cost, planes, lowest);
+  if (per_pixel) SRCV_LAUNCH(argmax_kernel<true>, blocks, threads, 0, stream, s, cost, planes, lowest);
+  else SRCV_LAUNCH(argmax_kernel<false>, blocks, threads, 0, stream, s, cost, planes, lowest);
   note_launch();
   return cudaGetLastError();
 }
-
 }  // namespace srcv

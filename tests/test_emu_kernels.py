@@ -1,0 +1,196 @@
+"""The product's SIMT kernels and C-ABI front end, compiled for the HOST (tests/emu: one
+std::thread per CUDA thread, std::barrier for __syncthreads, NaN-poisoned shared memory)
+and checked against the oracle — kernel-source parity in the CPU tier.
+
+What this covers that the `-m gpu` tests cannot cover here (no GPU in this container):
+indexing, barrier placement, launch heuristics (plane-loop split + last-arriver argmax of the
+dot sweep, persistent grid of the MLP backward), workspace carving and argument validation of
+every entry point of include/srcv_b200.h except the tcgen05 variant.  What it cannot cover:
+hardware limits, registers, speed — and device intrinsics are replaced by IEEE host math, so
+tolerances are the parity tolerances of tests/parity.py, not bit-exactness.
+scripts/emu_sanitize.sh runs this file under ThreadSanitizer (shared-memory races) and
+AddressSanitizer (out-of-bounds accesses)."""
+import ctypes as C
+
+import pytest
+import torch
+
+from oracle import costvolume_oracle as O
+from simplerecon_b200 import _native as N
+from simplerecon_b200.synthetic import make_tuple, mlp_state
+from tests import emu
+from tests.parity import assert_cost_close, assert_lowest_close, assert_mask_close
+
+
+@pytest.fixture(scope="module")
+def lib():
+    lib = emu.load()
+    yield lib
+    lib.emu_set_sms(4)
+    lib.srcv_set_variant(N.VARIANT_AUTO)
+
+
+def _weights(K, C, hidden=(128, 128), seed=1):
+    sd = mlp_state(views=K, channels=C, hidden=hidden, seed=seed)
+    return [sd[f"mlp.net.{i}.{n}"].clone() for i in (0, 2, 4) for n in ("weight", "bias")]
+
+
+def _rel(a, b):
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+# ----------------------------------------------------------------------------------------- #
+# dot-product sweep                                                                          #
+# ----------------------------------------------------------------------------------------- #
+@pytest.mark.parametrize("B,K,C,H,W,D,sms,variant,expect", [
+    (1, 2, 8, 10, 12, 5, 4, N.VARIANT_AUTO, "dot_generic"),            # C != 16: planar scalar gathers
+    (2, 3, 16, 12, 16, 16, 4, N.VARIANT_AUTO, "dot_fast_c4planar"),    # plane loop not split: argmax in the sweep
+    (2, 3, 16, 12, 16, 16, 148, N.VARIANT_AUTO, "dot_fast_c4planar"),  # split x2: last-arriver argmax
+    (1, 2, 16, 9, 21, 32, 148, N.VARIANT_AUTO, "dot_fast_c4planar"),   # split x4, ragged tiles, HW % 4 != 0
+    (1, 1, 16, 6, 40, 7, 4, N.VARIANT_AUTO, "dot_fast_c4planar"),      # one view, D not a multiple of the plane chunk
+    (1, 2, 16, 12, 16, 6, 4, N.VARIANT_GENERIC, "dot_generic"),        # forced generic on a fast-capable shape
+])
+def test_dot_forward(lib, B, K, C, H, W, D, sms, variant, expect):
+    lib.emu_set_sms(sms)
+    lib.srcv_set_variant(variant)
+    t = make_tuple(B, K, H, W, channels=C, seed=11 + D)
+    cost, lowest, planes_bd, used = emu.dot_forward(t, D)
+    assert used == expect
+    oc, ol, op, _ = O.forward_dot(**t, num_depth_bins=D)
+    assert_cost_close("dot", cost, oc, what=f"emu {used}")
+    assert_lowest_close("dot", lowest, planes_bd.view(B, D, 1, 1), oc, what=f"emu {used}")
+    assert _rel(planes_bd, op[:, :, 0, 0]) < 1e-6
+    # the argmax is exactly the argmax of the kernel's own volume (fused / last-arriver / separate launch)
+    idx = cost.argmax(1, keepdim=True)
+    assert torch.equal(torch.gather(planes_bd.view(B, D, 1, 1).expand_as(cost), 1, idx).squeeze(1), lowest)
+
+
+@pytest.mark.parametrize("C,sms", [(8, 4), (16, 4), (16, 148)])
+def test_dot_forward_per_pixel_planes(lib, C, sms):
+    lib.emu_set_sms(sms)
+    lib.srcv_set_variant(N.VARIANT_AUTO)
+    B, K, H, W, D = 1, 2, 10, 14, 16
+    t = make_tuple(B, K, H, W, channels=C, seed=5)
+    planes = 0.3 + 4.0 * torch.rand(B, D, H, W, generator=torch.Generator().manual_seed(6))
+    cost, lowest, _, used = emu.dot_forward(t, D, planes=planes)
+    oc, ol, _, _ = O.forward_dot(**t, num_depth_bins=D, depth_planes_bdhw=planes)
+    assert_cost_close("dot", cost, oc, what=f"emu per-pixel {used}")
+    assert_lowest_close("dot", lowest, planes, oc, what=f"emu per-pixel {used}")
+
+
+@pytest.mark.parametrize("B,K,C,H,W,D,per_pixel", [(2, 3, 16, 10, 12, 5, False), (1, 2, 8, 9, 11, 4, True)])
+def test_dot_backward(lib, B, K, C, H, W, D, per_pixel):
+    t = make_tuple(B, K, H, W, channels=C, seed=71)
+    g = torch.Generator().manual_seed(72)
+    gcost = torch.randn(B, D, H, W, generator=g)
+    planes = (0.3 + 4.0 * torch.rand(B, D, H, W, generator=g)) if per_pixel else None
+    tc = dict(t)
+    tc["cur_feats"] = t["cur_feats"].clone().requires_grad_(True)
+    tc["src_feats"] = t["src_feats"].clone().requires_grad_(True)
+    oc, _, op, _ = O.forward_dot(**tc, num_depth_bins=D, depth_planes_bdhw=planes)
+    (oc * gcost).sum().backward()
+    gcur, gsrc = emu.dot_backward(t, D, gcost, planes=planes if per_pixel else op[:, :, 0, 0].detach())
+    assert _rel(gcur, tc["cur_feats"].grad) < 5e-5
+    assert _rel(gsrc, tc["src_feats"].grad) < 5e-5
+
+
+def test_warp_features(lib):
+    B, K, C, H, W = 2, 3, 8, 9, 13
+    t = make_tuple(B, K, H, W, channels=C, seed=41)
+    plane = torch.tensor([1.3, 2.1])
+    warped, depths, mask = emu.warp_features(t, plane, per_pixel=False)
+    X = plane.view(B, 1, 1) * O.backproject_rays(t["cur_invK"], H, W)
+    px, py, zp = O.project(X, t["src_Ks"], t["src_extrinsics"])
+    ref = O.sample_bilinear_zeros(t["src_feats"], px, py).reshape(B, K, C, H, W)
+    assert (warped - ref).abs().max().item() <= 4e-5 * ref.abs().max().item() + 1e-6
+    assert _rel(depths, zp.reshape(B, K, H, W)) < 1e-5
+    assert ((mask > 0.5) != (zp.reshape(B, K, H, W) > 0)).float().mean().item() < 1e-3
+
+
+# ----------------------------------------------------------------------------------------- #
+# metadata-MLP sweep (fp32 SIMT variant) and its backward                                     #
+# ----------------------------------------------------------------------------------------- #
+@pytest.mark.parametrize("B,K,C,H,W,D,hidden,per_pixel", [
+    (1, 2, 8, 10, 12, 3, (128, 128), False),
+    (1, 7, 16, 8, 9, 2, (128, 128), False),       # hero channel count (202), ragged last tile
+    (2, 3, 16, 9, 11, 2, (96, 64), True),
+])
+def test_mlp_forward(lib, B, K, C, H, W, D, hidden, per_pixel):
+    lib.srcv_set_variant(N.VARIANT_AUTO)
+    t = make_tuple(B, K, H, W, channels=C, seed=21)
+    wts = _weights(K, C, hidden)
+    planes = (0.3 + 4.0 * torch.rand(B, D, H, W, generator=torch.Generator().manual_seed(22))) if per_pixel else None
+    cost, lowest, planes_bd, mask, used = emu.mlp_forward(t, D, wts, planes=planes)
+    assert used == "mlp_generic_fp32"
+    oc, ol, op, om = O.forward_mlp(**t, weights=tuple(wts), num_depth_bins=D, depth_planes_bdhw=planes,
+                                   return_mask=True)
+    assert_cost_close("mlp", cost, oc, what="emu mlp_generic")
+    assert_lowest_close("mlp", lowest, planes if per_pixel else planes_bd.view(B, D, 1, 1), oc, what="emu mlp_generic")
+    assert_mask_close(mask, om, what="emu mlp_generic")
+
+
+@pytest.mark.parametrize("B,K,C,H,W,D,hidden,per_pixel,sms", [
+    (1, 2, 8, 10, 12, 3, (128, 128), False, 2),    # F = 48 -> 64-wide feature tile; CTAs loop over tiles
+    (1, 7, 16, 8, 8, 2, (128, 128), False, 4),     # hero layout: F = 202 -> 208
+    (2, 3, 16, 9, 11, 2, (96, 64), True, 3),       # F = 98 -> 128; narrow hidden layers; ragged tiles
+])
+def test_mlp_backward(lib, B, K, C, H, W, D, hidden, per_pixel, sms):
+    """srcv_mlp_backward_f32 against autograd through the oracle (the composite the reference
+    differentiates, modules/cost_volume.py:451-736 + modules/networks.py:129-147)."""
+    lib.emu_set_sms(sms)
+    t = make_tuple(B, K, H, W, channels=C, seed=3)
+    wts = _weights(K, C, hidden)
+    g = torch.Generator().manual_seed(4)
+    gcost = torch.randn(B, D, H, W, generator=g)
+    planes = (0.3 + 4.0 * torch.rand(B, D, H, W, generator=g)) if per_pixel else None
+    tc = dict(t)
+    tc["cur_feats"] = t["cur_feats"].clone().requires_grad_(True)
+    tc["src_feats"] = t["src_feats"].clone().requires_grad_(True)
+    wo = [w.clone().requires_grad_(True) for w in wts]
+    oc, _, op, _ = O.forward_mlp(**tc, weights=tuple(wo), num_depth_bins=D, depth_planes_bdhw=planes)
+    (oc * gcost).sum().backward()
+    ref = [tc["cur_feats"].grad, tc["src_feats"].grad] + [w.grad for w in wo]
+    ours = emu.mlp_backward(t, D, wts, gcost, planes=planes if per_pixel else op[:, :, 0, 0].detach())
+    for name, o, r in zip(("cur", "src", "w1", "b1", "w2", "b2", "w3", "b3"), ours, ref):
+        assert o.shape == r.shape
+        assert _rel(o, r) < 2e-5, f"grad {name}: rel err {_rel(o, r):.2e}"
+
+
+# ----------------------------------------------------------------------------------------- #
+# C-ABI argument validation (srcv_api.cu) — runs the real front end, no kernel is launched    #
+# ----------------------------------------------------------------------------------------- #
+def test_api_validation(lib):
+    t = make_tuple(1, 2, 8, 10, channels=16, seed=1)
+    c = emu.Call(t, 4)
+    cost, lowest = torch.empty(1, 4, 8, 10), torch.empty(1, 8, 10)
+    n = lib.srcv_dot_workspace_bytes(C.byref(c.shape))
+    ws = c.workspace(n)
+    p = emu._p
+
+    def call(shape=c.shape, cur=t["cur_feats"], ws_=ws, nbytes=n, pl=c.pl, cams=c.cams):
+        return lib.srcv_dot_forward_f32(C.byref(shape), p(cur), p(c.t["src_feats"]), C.byref(cams), C.byref(pl),
+                                        p(cost), p(lowest), p(ws_), nbytes, None)
+
+    assert call() == 0
+    assert call(nbytes=n - 1) != 0 and b"workspace too small" in lib.srcv_last_error()
+    assert call(ws_=ws[16:]) != 0 and b"256-byte aligned" in lib.srcv_last_error()
+    assert call(cur=None) != 0
+    assert call(shape=N.Shape(1, 2, 16, 8, 0, 4)) != 0 and b"non-positive" in lib.srcv_last_error()
+    bad = N.Planes()
+    bad.mode = 9
+    assert call(pl=bad) != 0 and b"unknown planes mode" in lib.srcv_last_error()
+    assert call(cams=N.Cameras(None, None, None, None)) != 0
+    # unaligned feature pointer (the kernels use 16-byte vector loads)
+    assert call(cur=c.t["cur_feats"].reshape(-1)[1:]) != 0 and b"16-byte aligned" in lib.srcv_last_error()
+    # forcing the fast variant on a shape it does not support is an error, not a silent fallback
+    t8 = make_tuple(1, 2, 8, 10, channels=8, seed=2)
+    lib.srcv_set_variant(N.VARIANT_FAST)
+    with pytest.raises(N.SrcvError):
+        emu.dot_forward(t8, 4)
+    lib.srcv_set_variant(N.VARIANT_AUTO)
+    assert lib.srcv_set_variant(77) != 0
+    # MLP: hidden widths beyond the build, inconsistent workspace query
+    w = N.MlpWeights(1, 1, 1, 1, 1, 1, 256, 128)
+    assert lib.srcv_mlp_workspace_bytes(C.byref(c.shape), C.byref(w)) == 0
+    assert lib.srcv_mlp_backward_workspace_bytes(C.byref(N.Shape(1, 12, 16, 8, 10, 4)),
+                                                 C.byref(N.MlpWeights(1, 1, 1, 1, 1, 1, 128, 128))) == 0   # F = 332 > 208

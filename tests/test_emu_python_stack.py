@@ -1,0 +1,152 @@
+"""The Python layer (manager classes, autograd Functions, ctypes marshalling) driven on the
+CPU against the host-emulated C-ABI library (tests/emu), checked against the oracle.
+
+The product refuses CPU tensors (`cost_volume._require_cuda`) and loads only the nvcc-built
+library; this test monkeypatches exactly those two things — the device gate and the loaded
+library handle — plus the torch.cuda calls the managers make (and the workspace alignment a CUDA allocation has), so that the very same
+`forward` / autograd code that runs on the GPU runs here.  Nothing in the product takes this
+path by itself."""
+import contextlib
+import types
+
+import pytest
+import torch
+
+import simplerecon_b200 as S
+from oracle import costvolume_oracle as O
+from simplerecon_b200 import _native, cost_volume
+from simplerecon_b200.synthetic import make_tuple, mlp_state
+from tests import emu
+from tests.parity import assert_cost_close, assert_lowest_close, assert_mask_close
+
+
+@pytest.fixture()
+def emulated(monkeypatch):
+    lib = emu.load()
+    lib.emu_set_sms(4)
+    lib.srcv_set_variant(_native.VARIANT_AUTO)
+    monkeypatch.setattr(_native, "_lib", lib)
+    monkeypatch.setattr(cost_volume, "_require_cuda", lambda dev: None)
+    monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda dev=None: types.SimpleNamespace(cuda_stream=0))
+    # CUDA allocations are >= 256-byte aligned (the C ABI requires it of the workspace); CPU ones are not
+    real_empty = torch.empty
+
+    def aligned_empty(*size, **kw):
+        if kw.get("dtype") is torch.uint8 and len(size) == 1 and isinstance(size[0], int):
+            buf = real_empty(size[0] + 256, **kw)
+            off = (-buf.data_ptr()) % 256
+            return buf[off:off + size[0]]
+        return real_empty(*size, **kw)
+
+    monkeypatch.setattr(torch, "empty", aligned_empty)
+    return lib
+
+
+def _rel(a, b):
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+def _hero(K, C, H, W, D, fast=False):
+    cls = S.FastFeatureVolumeManager if fast else S.FeatureVolumeManager
+    m = cls(H, W, num_depth_bins=D, mlp_channels=[0, 128, 128, 1], matching_dim_size=C, num_source_views=K)
+    m.load_state_dict({**m.state_dict(), **mlp_state(views=K, channels=C, seed=1)})
+    return m
+
+
+def test_dot_manager_forward_and_training(emulated):
+    B, K, C, H, W, D = 2, 3, 16, 10, 12, 8
+    t = make_tuple(B, K, H, W, channels=C, seed=7)
+    m = S.CostVolumeManager(H, W, num_depth_bins=D)
+    with torch.no_grad():
+        cost, lowest, planes, mask = m(**t)
+    oc, ol, op, _ = O.forward_dot(**t, num_depth_bins=D)
+    assert mask is None and planes.shape == (B, D, H, W) and planes.stride()[2:] == (0, 0)
+    assert_cost_close("dot", cost, oc, what="manager/emu")
+    assert_lowest_close("dot", lowest, planes, oc, what="manager/emu")
+    # training path: _DotVolumeFunction
+    g = torch.randn(B, D, H, W, generator=torch.Generator().manual_seed(8))
+    ours, ref = dict(t), dict(t)
+    for d in (ours, ref):
+        d["cur_feats"] = t["cur_feats"].clone().requires_grad_(True)
+        d["src_feats"] = t["src_feats"].clone().requires_grad_(True)
+    c2, l2, _, _ = m(**ours)
+    assert c2.requires_grad and not l2.requires_grad and torch.equal(c2.detach(), cost)
+    (c2 * g).sum().backward()
+    rc, *_ = O.forward_dot(**ref, num_depth_bins=D)
+    (rc * g).sum().backward()
+    for k in ("cur_feats", "src_feats"):
+        assert _rel(ours[k].grad, ref[k].grad) < 5e-5, k
+
+
+@pytest.mark.parametrize("fast,return_mask", [(False, True), (True, False)])
+def test_hero_manager_forward(emulated, fast, return_mask):
+    B, K, C, H, W, D = 1, 3, 8, 9, 11, 3
+    t = make_tuple(B, K, H, W, channels=C, seed=9)
+    m = _hero(K, C, H, W, D, fast)
+    with torch.no_grad():
+        cost, lowest, planes, mask = m(**t, return_mask=return_mask)
+    wts = O.mlp_weights_from_state_dict(m.state_dict())
+    oc, ol, op, om = O.forward_mlp(**t, weights=wts, num_depth_bins=D, return_mask=True)
+    assert_cost_close("mlp", cost, oc, what="hero manager/emu")
+    assert_lowest_close("mlp", lowest, planes, oc, what="hero manager/emu")
+    if return_mask:
+        assert mask.dtype == torch.bool
+        assert_mask_close(mask, om, what="hero manager/emu")
+    else:
+        assert mask is None
+
+
+@pytest.mark.parametrize("per_pixel", [False, True])
+def test_hero_manager_training(emulated, per_pixel):
+    """FeatureVolumeManager under autograd: _MlpVolumeFunction -> srcv_mlp_backward_f32; gradients
+    of both feature inputs and all six MLP parameters against autograd through the oracle."""
+    B, K, C, H, W, D = 1, 2, 8, 8, 10, 3
+    t = make_tuple(B, K, H, W, channels=C, seed=13)
+    g = torch.Generator().manual_seed(14)
+    gcost = torch.randn(B, D, H, W, generator=g)
+    planes = (0.3 + 4.0 * torch.rand(B, D, H, W, generator=g)) if per_pixel else None
+    m = _hero(K, C, H, W, D).train()
+    ours = dict(t)
+    ours["cur_feats"] = t["cur_feats"].clone().requires_grad_(True)
+    ours["src_feats"] = t["src_feats"].clone().requires_grad_(True)
+    cost, lowest, planes_ret, mask = m(**ours, depth_planes_bdhw=planes, return_mask=True)
+    assert cost.requires_grad and not lowest.requires_grad and mask.dtype == torch.bool and not mask.requires_grad
+    (cost * gcost).sum().backward()
+    ref = dict(t)
+    ref["cur_feats"] = t["cur_feats"].clone().requires_grad_(True)
+    ref["src_feats"] = t["src_feats"].clone().requires_grad_(True)
+    wo = [w.detach().clone().requires_grad_(True) for w in O.mlp_weights_from_state_dict(m.state_dict())]
+    oc, *_ = O.forward_mlp(**ref, weights=tuple(wo), num_depth_bins=D, depth_planes_bdhw=planes)
+    (oc * gcost).sum().backward()
+    assert_cost_close("mlp", cost, oc.detach(), what="hero training forward")
+    assert _rel(ours["cur_feats"].grad, ref["cur_feats"].grad) < 2e-5
+    assert _rel(ours["src_feats"].grad, ref["src_feats"].grad) < 2e-5
+    params = [p for i in (0, 2, 4) for p in (m.mlp.net[i].weight, m.mlp.net[i].bias)]
+    for p, w in zip(params, wo):
+        assert p.grad is not None and p.grad.shape == w.grad.shape
+        assert _rel(p.grad, w.grad) < 2e-5
+    # only the MLP parameters require grad (features detached): still differentiable
+    m.zero_grad()
+    c3, *_ = m(**t, depth_planes_bdhw=planes)
+    assert c3.requires_grad
+    (c3 * gcost).sum().backward()
+    assert _rel(m.mlp.net[0].weight.grad, wo[0].grad) < 2e-5
+    # inference calls on the same manager take the plain fused path
+    with torch.no_grad():
+        c4, *_ = m(**t, depth_planes_bdhw=planes)
+    assert not c4.requires_grad and torch.equal(c4, cost.detach())
+
+
+def test_warp_features_method(emulated):
+    B, K, C, H, W = 1, 2, 8, 9, 12
+    t = make_tuple(B, K, H, W, channels=C, seed=15)
+    m = S.CostVolumeManager(H, W, num_depth_bins=4)
+    plane = torch.full((B, 1, 1, 1), 1.7).expand(B, 1, H, W)
+    world, depths, warped, mask = m.warp_features(t["src_feats"].reshape(B * K, C, H, W), t["src_extrinsics"],
+                                                  t["src_Ks"], t["cur_invK"], plane, B, K, C)
+    X = 1.7 * O.backproject_rays(t["cur_invK"], H, W)
+    px, py, zp = O.project(X, t["src_Ks"], t["src_extrinsics"])
+    ref = O.sample_bilinear_zeros(t["src_feats"], px, py).reshape(B, K, C, H, W)
+    assert (warped - ref).abs().max().item() <= 4e-5 * ref.abs().max().item() + 1e-6
+    assert world.shape == (B * K, 4, H * W)
