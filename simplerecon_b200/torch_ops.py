@@ -3,7 +3,7 @@
 SURVEY.md §8b asks, next to the C ABI, for a torch-library registration so the sweeps can
 be called as ``torch.ops.b200cv.dot_forward(...)`` / ``mlp_forward(...)``: they then have a
 schema, a fake (meta) kernel for shape propagation under ``FakeTensorMode`` /
-``torch.compile`` / ``torch.export``, and (dot) an autograd formula, and they work under
+``torch.compile`` / ``torch.export``, and an autograd formula, and they work under
 ``torch.inference_mode()``.  Only a CUDA kernel is registered for each: called with CPU
 tensors they raise ``NotImplementedError`` from the dispatcher — there is no fallback.
 
@@ -18,6 +18,8 @@ Every CUDA kernel here is one call into ``libsrcv_b200.so`` (include/srcv_b200.h
 ``b200cv::mlp_forward``           ``srcv_mlp_forward_f32``  — reference
                                   ``FeatureVolumeManager.build_cost_volume`` (:451-736) /
                                   ``FastFeatureVolumeManager.build_cost_volume`` (:967-1164)
+``b200cv::mlp_backward``          ``srcv_mlp_backward_f32`` — autograd of the same composite
+                                  w.r.t. the two feature inputs and the six MLP parameters
 ================================  ==========================================================
 
 ``planes`` is either ``(B, D)`` (one depth per plane, the reference's default log-spaced
@@ -35,7 +37,7 @@ from torch import Tensor
 
 from . import _native
 
-__all__ = ["dot_forward", "dot_backward", "mlp_forward"]
+__all__ = ["dot_forward", "dot_backward", "mlp_forward", "mlp_backward"]
 
 
 # ---------------------------------------------------------------------------------------------
@@ -225,3 +227,66 @@ def _(cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK, planes,
     _check_mlp(K, Cc, w1, b1, w2, b2, w3, b3)
     return (src_feats.new_empty((B, D, H, W)), src_feats.new_empty((B, H, W)),
             src_feats.new_empty((B, H, W), dtype=torch.bool))
+
+
+@torch.library.custom_op("b200cv::mlp_backward", mutates_args=(), device_types="cuda")
+def mlp_backward(grad_cost: Tensor, cur_feats: Tensor, src_feats: Tensor, src_extrinsics: Tensor,
+                 src_poses: Tensor, src_Ks: Tensor, cur_invK: Tensor, planes: Tensor, w1: Tensor, b1: Tensor,
+                 w2: Tensor, b2: Tensor, w3: Tensor, b3: Tensor
+                 ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """``(dL/dcur_feats, dL/dsrc_feats, dL/dw1, dL/db1, dL/dw2, dL/db2, dL/dw3, dL/db3)`` given
+    ``dL/dcost`` — a recompute kernel: nothing of the forward is needed but its inputs."""
+    B, K, Cc, H, W, D, per_pixel = _check_shapes(cur_feats, src_feats, src_extrinsics, src_Ks, cur_invK,
+                                                 planes, src_poses)
+    h1, h2 = _check_mlp(K, Cc, w1, b1, w2, b2, w3, b3)
+    if tuple(grad_cost.shape) != (B, D, H, W) or grad_cost.dtype != torch.float32:
+        raise ValueError(f"grad_cost must be float32 {(B, D, H, W)}")
+    lib = _native.load()
+    dev = src_feats.device
+    g, cur, src, E, P, Ks, invK, pln = map(
+        _c16, (grad_cost, cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK, planes))
+    ws_t = [_c16(t.detach()) for t in (w1, b1, w2, b2, w3, b3)]
+    shape = _native.Shape(B, K, Cc, H, W, D)
+    cams = _native.Cameras(E.data_ptr(), P.data_ptr(), Ks.data_ptr(), invK.data_ptr())
+    pl = _planes_struct(pln, per_pixel)
+    w = _native.MlpWeights(*[t.data_ptr() for t in ws_t], h1, h2)
+    with torch.cuda.device(dev):
+        gcur, gsrc = torch.empty_like(cur), torch.empty_like(src)
+        gw = [torch.empty_like(t) for t in ws_t]
+        grads = _native.MlpGrads(*[t.data_ptr() for t in gw])
+        n = lib.srcv_mlp_backward_workspace_bytes(C.byref(shape), C.byref(w))
+        if n == 0:
+            raise NotImplementedError("metadata-MLP backward: at most 208 input features, hidden widths <= 128")
+        ws = torch.empty(n, device=dev, dtype=torch.uint8)
+        _native.check(lib.srcv_mlp_backward_f32(
+            C.byref(shape), _ptr(cur), _ptr(src), C.byref(cams), C.byref(pl), C.byref(w), _ptr(g), _ptr(gcur),
+            _ptr(gsrc), C.byref(grads), _ptr(ws), n, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return (gcur, gsrc, *gw)
+
+
+@mlp_backward.register_fake
+def _(grad_cost, cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK, planes, w1, b1, w2, b2, w3, b3):
+    B, K, Cc, H, W, D, _pp = _check_shapes(cur_feats, src_feats, src_extrinsics, src_Ks, cur_invK, planes,
+                                           src_poses)
+    _check_mlp(K, Cc, w1, b1, w2, b2, w3, b3)
+    c = torch.contiguous_format
+    return tuple(torch.empty_like(t, memory_format=c) for t in (cur_feats, src_feats, w1, b1, w2, b2, w3, b3))
+
+
+def _mlp_setup_context(ctx, inputs, output):
+    ctx.save_for_backward(*inputs)
+    ctx.mark_non_differentiable(output[1], output[2])      # lowest_cost (argmax), overall mask (bool)
+
+
+def _mlp_autograd(ctx, grad_cost, _grad_lowest, _grad_mask):
+    cur, src, E, P, Ks, invK, planes, w1, b1, w2, b2, w3, b3 = ctx.saved_tensors
+    need = ctx.needs_input_grad
+    g = [None] * 13
+    if any(need[i] for i in (0, 1, 7, 8, 9, 10, 11, 12)):
+        out = mlp_backward(grad_cost.contiguous(), cur, src, E, P, Ks, invK, planes, w1, b1, w2, b2, w3, b3)
+        g[0], g[1] = out[0], out[1]
+        g[7:13] = out[2:8]
+    return tuple(g)
+
+
+mlp_forward.register_autograd(_mlp_autograd, setup_context=_mlp_setup_context)

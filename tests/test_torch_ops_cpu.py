@@ -34,6 +34,8 @@ def test_schemas():
     assert "Tensor src_poses" in s and "Tensor w3, Tensor b3" in s and s.endswith("-> (Tensor, Tensor, Tensor)")
     s = str(torch.ops.b200cv.dot_backward.default._schema)
     assert s.startswith("b200cv::dot_backward(Tensor grad_cost") and s.endswith("-> (Tensor, Tensor)")
+    s = str(torch.ops.b200cv.mlp_backward.default._schema)
+    assert s.startswith("b200cv::mlp_backward(Tensor grad_cost") and s.count("Tensor") == 14 + 8
 
 
 @pytest.mark.parametrize("per_pixel", [False, True])
@@ -63,6 +65,21 @@ def test_autograd_wiring_on_meta():
     assert cost.requires_grad and not lowest.requires_grad      # lowest comes from an argmax
     cost.sum().backward()
     assert cur.grad.shape == cur.shape and src.grad.shape == src.shape
+
+
+def test_mlp_autograd_wiring_on_meta():
+    args = list(mlp_args())
+    for i in (0, 1, 7, 8, 9, 10, 11, 12):            # features and the six MLP parameters
+        args[i].requires_grad_(True)
+    cost, lowest, mask = torch.ops.b200cv.mlp_forward(*args)
+    assert cost.requires_grad and not lowest.requires_grad and not mask.requires_grad
+    cost.sum().backward()
+    for i in (0, 1, 7, 8, 9, 10, 11, 12):
+        assert args[i].grad is not None and args[i].grad.shape == args[i].shape
+    for i in (2, 3, 4, 5, 6):                        # cameras and planes: no gradient
+        assert args[i].grad is None
+    outs = torch.ops.b200cv.mlp_backward(m(B, D, H, W), *mlp_args())
+    assert [tuple(o.shape) for o in outs] == [tuple(a.shape) for j, a in enumerate(mlp_args()) if j in (0, 1, 7, 8, 9, 10, 11, 12)]
 
 
 def test_validation():
