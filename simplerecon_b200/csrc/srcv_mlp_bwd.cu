@@ -72,32 +72,60 @@ mlp_bwd_pack_kernel(const float* __restrict__ w1, const float* __restrict__ w2, 
   }
 }
 
-// acc[ii][i] += sum_k A[k][4 ty + ii] * Wg[k][tx + 16 i]   for k in [0, nk),
-// A a shared tile [k][BTP], Wg a global (nk, 16 NI) image streamed through a
-// double-buffered BKC-row chunk.  Ends with a block sync.
+// Column owned by slot i of thread-column tx in gemm_rows<NI>: NI/4 groups of four adjacent
+// columns (one 16-byte shared-memory read per group and k) plus NI%4 single columns.
+template <int NI>
+__device__ __forceinline__ int gemm_col(int i, int tx) {
+  constexpr int NV = NI / 4;
+  return i < 4 * NV ? (i >> 2) * 64 + tx * 4 + (i & 3) : NV * 64 + (i - 4 * NV) * 16 + tx;
+}
+
+// acc[ii][i] += sum_k A[k][4 ty + ii] * Wg[k][gemm_col<NI>(i, tx)]   for k in [0, nk),
+// A a shared tile [k][BTP], Wg a global (nk, 16 NI) image streamed through a double-buffered
+// BKC-row chunk (next chunk prefetched into registers while this one is used).  Ends with a
+// block sync.
 template <int NI>
 __device__ __forceinline__ void gemm_rows(float (&acc)[4][NI], const float* __restrict__ sA,
                                           float* __restrict__ sW, const float* __restrict__ wg, int nk) {
   constexpr int ncols = 16 * NI;
-  constexpr int chunk = BKC * ncols;
+  constexpr int NV = NI / 4;
+  constexpr int nvec = BKC * ncols / 4;                 // 16-byte vectors per chunk
+  constexpr int PER = (nvec + BNT - 1) / BNT;           // per thread: 1 or 2
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float4 nxt[PER];
+#pragma unroll
+  for (int v = 0; v < PER; ++v)
+    if (tid + v * BNT < nvec) nxt[v] = __ldg(reinterpret_cast<const float4*>(wg) + tid + v * BNT);
   int buf = 0;
   for (int k0 = 0; k0 < nk; k0 += BKC) {
     float* wb = sW + buf * (BKC * BFMAX);
-    for (int i = tid * 4; i < chunk; i += BNT * 4)
-      *reinterpret_cast<float4*>(wb + i) =
-          __ldg(reinterpret_cast<const float4*>(wg + (size_t)k0 * ncols + i));
+#pragma unroll
+    for (int v = 0; v < PER; ++v)
+      if (tid + v * BNT < nvec) reinterpret_cast<float4*>(wb)[tid + v * BNT] = nxt[v];
     __syncthreads();   // chunk visible; also: everyone is past the reads of the buffer written next
+    if (k0 + BKC < nk) {
+#pragma unroll
+      for (int v = 0; v < PER; ++v)
+        if (tid + v * BNT < nvec)
+          nxt[v] = __ldg(reinterpret_cast<const float4*>(wg + (size_t)(k0 + BKC) * ncols) + tid + v * BNT);
+    }
 #pragma unroll
     for (int kk = 0; kk < BKC; ++kk) {
       const float4 a = *reinterpret_cast<const float4*>(sA + (k0 + kk) * BTP + 4 * ty);
+      float w[NI];
+#pragma unroll
+      for (int q = 0; q < NV; ++q) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wb + kk * ncols + q * 64 + tx * 4);
+        w[4 * q] = w4.x; w[4 * q + 1] = w4.y; w[4 * q + 2] = w4.z; w[4 * q + 3] = w4.w;
+      }
+#pragma unroll
+      for (int i = 4 * NV; i < NI; ++i) w[i] = wb[kk * ncols + NV * 64 + (i - 4 * NV) * 16 + tx];
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
-        const float w = wb[kk * ncols + tx + 16 * i];
-        acc[0][i] = fmaf(a.x, w, acc[0][i]);
-        acc[1][i] = fmaf(a.y, w, acc[1][i]);
-        acc[2][i] = fmaf(a.z, w, acc[2][i]);
-        acc[3][i] = fmaf(a.w, w, acc[3][i]);
+        acc[0][i] = fmaf(a.x, w[i], acc[0][i]);
+        acc[1][i] = fmaf(a.y, w[i], acc[1][i]);
+        acc[2][i] = fmaf(a.z, w[i], acc[2][i]);
+        acc[3][i] = fmaf(a.w, w[i], acc[3][i]);
       }
     }
     buf ^= 1;
@@ -267,7 +295,7 @@ mlp_backward_kernel(srcv_shape s, BwdDims m, const float* __restrict__ cur,
     gemm_rows<8>(acc, sX, sW, w1t, Fp);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int n = tx + 16 * i;
+      const int n = gemm_col<8>(i, tx);
       const float bias = n < m.H1 ? __ldg(b1 + n) : 0.f;
       *reinterpret_cast<float4*>(sH1 + n * BTP + 4 * ty) =
           make_float4(leaky(acc[0][i] + bias), leaky(acc[1][i] + bias), leaky(acc[2][i] + bias),
@@ -285,7 +313,7 @@ mlp_backward_kernel(srcv_shape s, BwdDims m, const float* __restrict__ cur,
       const float4 g = *reinterpret_cast<const float4*>(sGo + 4 * ty);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int n = tx + 16 * i;
+        const int n = gemm_col<8>(i, tx);
         const bool live = n < m.H2;
         const float bias = live ? __ldg(b2 + n) : 0.f, w = live ? __ldg(w3 + n) : 0.f;
         const float a0 = acc[0][i] + bias, a1 = acc[1][i] + bias, a2 = acc[2][i] + bias, a3 = acc[3][i] + bias;
@@ -316,7 +344,7 @@ mlp_backward_kernel(srcv_shape s, BwdDims m, const float* __restrict__ cur,
     gemm_rows<8>(acc, sG, sW, w2p, BN);                         // k = n2, columns = n1
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int n = tx + 16 * i;
+      const int n = gemm_col<8>(i, tx);
       const float4 h = *reinterpret_cast<const float4*>(sH1 + n * BTP + 4 * ty);
       *reinterpret_cast<float4*>(sG + n * BTP + 4 * ty) =
           make_float4(acc[0][i] * (h.x > 0.f ? 1.f : kLeaky), acc[1][i] * (h.y > 0.f ? 1.f : kLeaky),
@@ -341,7 +369,7 @@ mlp_backward_kernel(srcv_shape s, BwdDims m, const float* __restrict__ cur,
       gemm_rows<NIF>(ax, sG, sW, w1p, BN);                      // k = n1, columns = f
 #pragma unroll
       for (int i = 0; i < NIF; ++i)
-        *reinterpret_cast<float4*>(sX + (tx + 16 * i) * BTP + 4 * ty) =
+        *reinterpret_cast<float4*>(sX + gemm_col<NIF>(i, tx) * BTP + 4 * ty) =
             make_float4(ax[0][i], ax[1][i], ax[2][i], ax[3][i]);
     }
     __syncthreads();

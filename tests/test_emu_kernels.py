@@ -19,7 +19,8 @@ from oracle import costvolume_oracle as O
 from simplerecon_b200 import _native as N
 from simplerecon_b200.synthetic import make_tuple, mlp_state
 from tests import emu
-from tests.parity import assert_cost_close, assert_lowest_close, assert_mask_close
+from tests.parity import (assert_cost_close, assert_lowest_close, assert_mask_close, golden_names,
+                          load_golden)
 
 
 @pytest.fixture(scope="module")
@@ -37,6 +38,40 @@ def _weights(K, C, hidden=(128, 128), seed=1):
 
 def _rel(a, b):
     return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+# ----------------------------------------------------------------------------------------- #
+# golden vectors of the unmodified reference (tests/golden), through the emulated C ABI       #
+# ----------------------------------------------------------------------------------------- #
+@pytest.mark.parametrize("variant", ["generic", "auto"])
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_through_emulated_abi(lib, name, variant):
+    """Same check as tests/test_gpu_parity.py::test_golden, on the host-compiled kernel sources:
+    reference fp32 / fp64 outputs, argmax depth and mask of every committed fixture."""
+    g, inputs, sd = load_golden(name)
+    kind, D = g["kind"], g["D"]
+    C_ = inputs["src_feats"].shape[2]
+    if variant == "auto" and (kind == "mlp" or C_ != 16):
+        pytest.skip("no second SIMT variant for this case (the tcgen05 kernel is GPU-only)")
+    lib.emu_set_sms(148 if variant == "auto" else 4)          # auto: exercise the plane-loop split
+    lib.srcv_set_variant(N.VARIANT_GENERIC if variant == "generic" else N.VARIANT_AUTO)
+    planes_in = inputs.get("depth_planes_bdhw")
+    B, H, W = inputs["src_feats"].shape[0], inputs["src_feats"].shape[3], inputs["src_feats"].shape[4]
+    if kind == "dot":
+        cost, lowest, planes_bd, used = emu.dot_forward(inputs, D, planes=planes_in)
+        mask = None
+    else:
+        wts = O.mlp_weights_from_state_dict(sd)
+        cost, lowest, planes_bd, mask, used = emu.mlp_forward(inputs, D, wts, planes=planes_in)
+    lib.srcv_set_variant(N.VARIANT_AUTO)
+    assert ("fast" in used) == (variant == "auto"), used
+    assert_cost_close(kind, cost, g["ref_cost"], g["ref_cost64"], what=f"emu {name}/{used}")
+    planes = planes_in if planes_in is not None else planes_bd.view(B, D, 1, 1)
+    if planes_in is None:
+        assert torch.allclose(planes_bd, g["ref_planes"], rtol=3e-7, atol=0)
+    assert_lowest_close(kind, lowest, planes, g["ref_cost"], what=f"emu {name}")
+    if kind == "mlp":
+        assert_mask_close(mask, g["ref_mask"], what=f"emu {name}")
 
 
 # ----------------------------------------------------------------------------------------- #
