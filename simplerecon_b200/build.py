@@ -41,23 +41,29 @@ def up_to_date() -> bool:
     return all(p.stat().st_mtime <= t for p in SRC + HDR)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and up_to_date():
+def build(force: bool = False, verbose: bool = False, out: Path | None = None, extra: list[str] | None = None) -> Path:
+    """``out`` / ``extra`` build an experiment variant next to the default library (e.g.
+    ``--out lib/libsrcv_b200_uw.so --extra=-DSRCV_TC_UNIFORM_WARP``; load it with
+    ``SRCV_B200_LIB=<path>``); the default build never takes extra flags."""
+    if out is None and not extra and not force and up_to_date():
         return OUT
-    OUT.parent.mkdir(parents=True, exist_ok=True)
-    cmd = [nvcc_path(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []),
-           "-o", str(OUT), *map(str, SRC)]
+    out = Path(out) if out else OUT
+    out.parent.mkdir(parents=True, exist_ok=True)
+    cmd = [nvcc_path(), *NVCC_FLAGS, *(extra or []), *(["-Xptxas", "-v"] if verbose else []),
+           "-o", str(out), *map(str, SRC)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed ({r.returncode}): {' '.join(cmd)}")
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--out", default=None, help="write an experiment variant here instead of the default library")
+    ap.add_argument("--extra", action="append", default=[], help="extra nvcc flag (repeatable), variants only")
     a = ap.parse_args()
-    print(build(a.force, a.verbose))
+    print(build(a.force, a.verbose, a.out, a.extra))

@@ -364,7 +364,17 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
   float* spart = reinterpret_cast<float*>(smem + kOffPart);
   const float* svec = reinterpret_cast<const float*>(smem + kOffVec);
 
+  // SRCV_TC_UNIFORM_WARP (round-2 experiment, off by default): taking the warp index through a
+  // shuffle broadcast tells ptxas the role branches below are warp-uniform, so the global-memory
+  // descriptor stays in uniform registers instead of being re-materialised with two R2UR before
+  // every LDG of the worker loop (static SASS of the 160x120 kernel: 441 -> 59 R2UR, 3784 -> 3464
+  // instructions, spill stores 82 -> 54 bytes).  Same value on every lane either way; not yet
+  // run on a GPU, hence not the default.
+#ifdef SRCV_TC_UNIFORM_WARP
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+#else
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#endif
   const int W = TW ? TW : s.W, H = TH ? TH : s.H, HW = W * H, D = s.D;
   constexpr int HWC = TW * TH;
   const int tiles_x = (W + kTileW - 1) / kTileW, tiles_xy = tiles_x * ((H + kTileH - 1) / kTileH);
