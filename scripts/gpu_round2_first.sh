@@ -34,4 +34,10 @@ echo "== 5. ncu: the MLP backward kernel (one launch, full sections)"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:mlp_backward_kernel -c 1 \
     -o $O/prof_r02_mlp_bwd python scripts/bench_backward.py --workload cfg2 --batch 1 --steps 1 --warmup 0 \
     > $O/r02_first_ncu_bwd.log 2>&1; echo "ncu rc=$?"
+echo "== 6. measured L1 gather ceiling for the dot sweep's load shape (scripts/probes)"
+if [ -x scripts/probes/l1_gather_probe ]; then
+  timeout 60 ./scripts/probes/l1_gather_probe | tee $O/r02_first_l1_probe.jsonl
+else
+  echo "build it first: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/probes/l1_gather_probe scripts/probes/l1_gather_probe.cu"
+fi
 ls -la $O | tail -n 12
