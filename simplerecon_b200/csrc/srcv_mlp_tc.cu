@@ -351,7 +351,7 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
               const ViewParams* __restrict__ views, const FrameParams* __restrict__ frames,
               const float* __restrict__ planes, const uint8_t* __restrict__ image,
               float* __restrict__ cost, uint8_t* __restrict__ mask_out, long long num_tiles) {
-  extern __shared__ __align__(1024) uint8_t smem[];
+  SRCV_DYNAMIC_SMEM_ALIGNED(uint8_t, smem, 1024);
   __shared__ uint32_t s_tmem_base;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* bar_a1_full = bars + 0;   // workers -> MMA: A1 of a tile is in TMEM      (512 arrivals)
@@ -497,6 +497,20 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
           acc = fmaf(leaky(fmaf(__uint_as_float(r[j + 3]), kWUnscale, bb.w)), ww.w, acc);
         }
       }
+#ifdef SRCV_TC_EARLY_FLAGS
+      // Mask bits of THIS tile, read before the bar_d_free arrival.  The four quarters wrote them
+      // before their bar_a1_full arrival, so they are visible since the bar_mma1 wait above; read
+      // here, the read is ordered (d_free -> MMA issue -> bar_mma1 of the next tile) before the
+      // write of the tile after next into the same parity slot.  Read late (below, the default
+      // until this variant has run on a GPU) that write is unordered with the read: found by
+      // ThreadSanitizer on the host emulation; on hardware the reader would have to stall for a
+      // whole MMA + epilogue (> 3 k clocks) between two adjacent instructions to lose the race.
+      unsigned tile_bits = 0;
+      if (q == 0 && mask_out != nullptr && cur_row.d == D - 1) {
+        const uint8_t* fl = sflag + (it & 1) * 4 * kRows + row;
+        tile_bits = fl[0] | fl[kRows] | fl[2 * kRows] | fl[3 * kRows];
+      }
+#endif
       fence_before_sync();
       mbar_arrive(bar_d_free);
       spart[((it & 1) * 4 + q) * kRows + row] = acc;
@@ -509,8 +523,12 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
         if (cur_row.active) {
           cost[((size_t)cur_row.b * D + cur_row.d) * HW + cur_row.p] = total + svec[3 * kN];
           if (mask_out != nullptr && cur_row.d == D - 1) {
+#ifdef SRCV_TC_EARLY_FLAGS
+            const unsigned bits = tile_bits;
+#else
             const uint8_t* fl = sflag + (it & 1) * 4 * kRows + row;
             const unsigned bits = fl[0] | fl[kRows] | fl[2 * kRows] | fl[3 * kRows];
+#endif
             mask_out[(size_t)cur_row.b * HW + cur_row.p] = (bits == 3u) ? 1 : 0;
           }
         }
@@ -566,7 +584,7 @@ tc_selftest_pack(const float* __restrict__ Wm, int Kp, __half* __restrict__ hi, 
 __global__ void __launch_bounds__(160, 1)
 tc_selftest_kernel(const float* __restrict__ A, const __half* __restrict__ whi,
                    const __half* __restrict__ wlo, int Kp, float* __restrict__ Dout) {
-  extern __shared__ __align__(1024) uint8_t smem[];
+  SRCV_DYNAMIC_SMEM_ALIGNED(uint8_t, smem, 1024);
   __shared__ uint32_t s_tmem_base;
   __shared__ uint64_t bar_a, bar_d;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -641,7 +659,7 @@ cudaError_t launch_mlp_tc(const srcv_shape& s, const float* cur, const Workspace
                           const float* planes, bool per_pixel, const srcv_mlp_weights& w, float* cost,
                           float* lowest, uint8_t* mask, cudaStream_t stream) {
   uint8_t* image = reinterpret_cast<uint8_t*>(ws.extra);
-  tc_pack_kernel<<<64, 256, 0, stream>>>(w, image);
+  SRCV_LAUNCH(tc_pack_kernel, 64, 256, 0, stream, w, image);
   note_launch();
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return err;
@@ -659,8 +677,8 @@ cudaError_t launch_mlp_tc(const srcv_shape& s, const float* cur, const Workspace
     err = cudaFuncSetAttribute(mlp_tc_kernel<PP, TW_, TH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                (int)kSmemBytes);                                                      \
     if (err != cudaSuccess) return err;                                                               \
-    mlp_tc_kernel<PP, TW_, TH_><<<grid, kThreads, kSmemBytes, stream>>>(                              \
-        s, cur4, src4, ws.views, ws.frames, planes, image, cost, mask, num_tiles);                    \
+    SRCV_LAUNCH((mlp_tc_kernel<PP, TW_, TH_>), grid, kThreads, kSmemBytes, stream,                    \
+                s, cur4, src4, ws.views, ws.frames, planes, image, cost, mask, num_tiles);            \
   } while (0)
 #define SRCV_TC_SIZES(PP)                                                   \
   if (s.W == 160 && s.H == 120) SRCV_TC_LAUNCH(PP, 160, 120);               \
@@ -683,12 +701,12 @@ cudaError_t launch_tc_selftest(const float* A, const float* Wm, int Kp, float* D
   if (Kp % 16 != 0 || Kp <= 0 || Kp > 256) return cudaErrorInvalidValue;
   __half* hi = reinterpret_cast<__half*>(scratch);
   __half* lo = hi + (size_t)kN * Kp;
-  tc_selftest_pack<<<32, 256, 0, stream>>>(Wm, Kp, hi, lo);
+  SRCV_LAUNCH(tc_selftest_pack, 32, 256, 0, stream, Wm, Kp, hi, lo);
   note_launch();
   const size_t smem = (size_t)2 * kN * Kp * 2;
   cudaError_t err = cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
-  tc_selftest_kernel<<<1, 160, smem, stream>>>(A, hi, lo, Kp, Dout);
+  SRCV_LAUNCH(tc_selftest_kernel, 1, 160, smem, stream, A, hi, lo, Kp, Dout);
   note_launch();
   return cudaGetLastError();
 }

@@ -13,6 +13,9 @@
 //     bytes core matrices; row r, K chunk c (8 halves) lives at
 //         c * LBO + (r / 8) * SBO + (r % 8) * 16   bytes from the start address.
 #pragma once
+#ifdef SRCV_HOST_EMU
+#include "emu_tc.h"   // tests/emu: functional host model of this layer (same names, same semantics)
+#else
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -203,3 +206,4 @@ __device__ __forceinline__ void split_pack(float even, float odd, uint32_t& hi, 
 
 }  // namespace tc
 }  // namespace srcv
+#endif  // SRCV_HOST_EMU

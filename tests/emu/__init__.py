@@ -10,10 +10,10 @@ REPO = HERE.parent.parent
 BUILD = HERE / "_build"
 CXX = "/usr/bin/g++" if Path("/usr/bin/g++").is_file() else "g++"
 CSRC = REPO / "simplerecon_b200" / "csrc"
-# every kernel file except the tcgen05 one, plus the C-ABI front end
+# every kernel file (the tcgen05 one against the functional model in emu_tc.h) plus the C-ABI front end
 UNITS = [CSRC / n for n in ("srcv_api.cu", "srcv_prep.cu", "srcv_dot.cu", "srcv_dot_bwd.cu",
-                            "srcv_mlp_generic.cu", "srcv_mlp_bwd.cu")]
-SOURCES = [HERE / "emu_driver.cpp", HERE / "emu_cuda.h", REPO / "include" / "srcv_b200.h", *sorted(CSRC.glob("*"))]
+                            "srcv_mlp_generic.cu", "srcv_mlp_bwd.cu", "srcv_mlp_tc.cu")]
+SOURCES = [HERE / "emu_driver.cpp", HERE / "emu_cuda.h", HERE / "emu_tc.h", REPO / "include" / "srcv_b200.h", *sorted(CSRC.glob("*"))]
 
 
 def build(sanitize: str | None = None, force: bool = False) -> Path:
@@ -24,7 +24,12 @@ def build(sanitize: str | None = None, force: bool = False) -> Path:
     out = BUILD / (f"libsrcv_emu_{sanitize}.so" if sanitize else "libsrcv_emu.so")
     if not force and out.is_file() and all(p.stat().st_mtime <= out.stat().st_mtime for p in SOURCES if p.is_file()):
         return out
-    flags = ["-std=c++20", "-pthread", "-fPIC", "-ffp-contract=off", "-DSRCV_HOST_EMU=1", f"-I{HERE}", "-w"]
+    # SRCV_TC_EARLY_FLAGS: the tcgen05 kernel with the mask-flag read moved before the bar_d_free
+    # arrival — the fix for the one (benign on hardware) unordered access ThreadSanitizer found in
+    # the default code; it becomes the nvcc default once it has run on a GPU.
+    # $SRCV_EMU_DEFINES overrides (e.g. "" to emulate exactly the shipped default).
+    defines = os.environ.get("SRCV_EMU_DEFINES", "-DSRCV_TC_EARLY_FLAGS").split()
+    flags = ["-std=c++20", "-pthread", "-fPIC", "-ffp-contract=off", "-DSRCV_HOST_EMU=1", *defines, f"-I{HERE}", "-w"]
     flags += ["-O1", "-g", f"-fsanitize={sanitize}"] if sanitize else ["-O2"]
     objs, procs = [], []
     for src in [HERE / "emu_driver.cpp", *UNITS]:          # one translation unit per source, in parallel

@@ -60,6 +60,7 @@ struct alignas(8) float2 { float x, y; };
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 inline float2 make_float2(float x, float y) { return float2{x, y}; }
 struct uint3 { unsigned x, y, z; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
 struct dim3 {
   unsigned x, y, z;
   dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
@@ -76,6 +77,8 @@ struct WarpVote {
   std::atomic<int> acc[3];
 };
 inline thread_local WarpVote* t_votes = nullptr;
+inline thread_local uint32_t* t_tmem = nullptr;        // tensor memory of the CTA (emu_tc.h)
+inline thread_local uint32_t* t_shfl = nullptr;        // per-warp exchange slots for __shfl_sync
 inline thread_local unsigned t_vote_round = 0;
 
 // Runs body() once per CUDA thread of a (grid x block) launch.
@@ -86,8 +89,9 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& body) {
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx = 0; bx < grid.x; ++bx) {
-        void* sm = std::aligned_alloc(128, bytes);
-        std::memset(sm, 0xFF, bytes);  // all-ones = NaN as float: uninitialised reads poison the result
+        void* sm = std::aligned_alloc(1024, ((bytes + 1023) / 1024) * 1024);
+        std::memset(sm, 0xFF, bytes);
+        std::vector<uint32_t> tmem(128 * 512, 0xFFFFFFFFu), shfl(((nthreads + 31) / 32) * 32, 0u);  // all-ones = NaN as float: uninitialised reads poison the result
         std::barrier<> bar((std::ptrdiff_t)nthreads);
         const unsigned nwarps = (nthreads + 31) / 32;
         std::vector<WarpVote> votes(nwarps);
@@ -108,6 +112,8 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& body) {
             t_smem = sm;
             t_bar = &bar;
             t_votes = votes.data();
+            t_tmem = tmem.data();
+            t_shfl = shfl.data();
             t_vote_round = 0;
             body();
             bar.arrive_and_drop();   // a CUDA thread that has exited no longer takes part in barriers
@@ -126,6 +132,11 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& body) {
 #define gridDim (::emu::t_gdim)
 
 inline void __syncthreads() { ::emu::t_bar->arrive_and_wait(); }
+inline void __syncwarp(unsigned = 0xffffffffu) {
+  ::emu::t_votes[(threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z)) / 32].bar->arrive_and_wait();
+}
+inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 
 template <class T> inline T __ldg(const T* p) { return *p; }
@@ -151,6 +162,18 @@ inline float atomicAdd(float* p, float v) {
 }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+
+// __shfl_sync over a full, converged warp (32-bit payloads)
+inline int __shfl_sync(unsigned, int v, int src_lane) {
+  const unsigned lin = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  ::emu::WarpVote& w = ::emu::t_votes[lin / 32];
+  uint32_t* slots = ::emu::t_shfl + (lin / 32) * 32;
+  slots[lin & 31] = (uint32_t)v;
+  w.bar->arrive_and_wait();
+  const int r = (int)slots[src_lane & 31];
+  w.bar->arrive_and_wait();                 // nobody overwrites a slot before everybody has read
+  return r;
+}
 
 // __all_sync over a full, converged warp (the only warp-level intrinsic the SIMT kernels use):
 // the 32 std::threads of the warp meet at a per-warp barrier; three rotating slots so that a

@@ -5,9 +5,11 @@ and checked against the oracle — kernel-source parity in the CPU tier.
 What this covers that the `-m gpu` tests cannot cover here (no GPU in this container):
 indexing, barrier placement, launch heuristics (plane-loop split + last-arriver argmax of the
 dot sweep, persistent grid of the MLP backward), workspace carving and argument validation of
-every entry point of include/srcv_b200.h except the tcgen05 variant.  What it cannot cover:
-hardware limits, registers, speed — and device intrinsics are replaced by IEEE host math, so
-tolerances are the parity tolerances of tests/parity.py, not bit-exactness.
+every entry point of include/srcv_b200.h — including the tcgen05 kernel, which runs against a
+functional model of TMEM / tcgen05.mma / mbarrier / bulk copy (tests/emu/emu_tc.h).  What it
+cannot cover: hardware limits, registers, speed, the asynchrony of tcgen05.ld/st — and device
+intrinsics are replaced by IEEE host math, so tolerances are the parity tolerances of
+tests/parity.py, not bit-exactness.
 scripts/emu_sanitize.sh runs this file under ThreadSanitizer (shared-memory races) and
 AddressSanitizer (out-of-bounds accesses)."""
 import ctypes as C
@@ -51,8 +53,9 @@ def test_golden_through_emulated_abi(lib, name, variant):
     g, inputs, sd = load_golden(name)
     kind, D = g["kind"], g["D"]
     C_ = inputs["src_feats"].shape[2]
-    if variant == "auto" and (kind == "mlp" or C_ != 16):
-        pytest.skip("no second SIMT variant for this case (the tcgen05 kernel is GPU-only)")
+    K_ = inputs["src_feats"].shape[1]
+    if variant == "auto" and (C_ != 16 or (kind == "mlp" and K_ != 7)):
+        pytest.skip("no second variant for this shape")
     lib.emu_set_sms(148 if variant == "auto" else 4)          # auto: exercise the plane-loop split
     lib.srcv_set_variant(N.VARIANT_GENERIC if variant == "generic" else N.VARIANT_AUTO)
     planes_in = inputs.get("depth_planes_bdhw")
@@ -64,7 +67,7 @@ def test_golden_through_emulated_abi(lib, name, variant):
         wts = O.mlp_weights_from_state_dict(sd)
         cost, lowest, planes_bd, mask, used = emu.mlp_forward(inputs, D, wts, planes=planes_in)
     lib.srcv_set_variant(N.VARIANT_AUTO)
-    assert ("fast" in used) == (variant == "auto"), used
+    assert (("fast" in used) or ("tcgen05" in used)) == (variant == "auto"), used
     assert_cost_close(kind, cost, g["ref_cost"], g["ref_cost64"], what=f"emu {name}/{used}")
     planes = planes_in if planes_in is not None else planes_bd.view(B, D, 1, 1)
     if planes_in is None:
@@ -151,11 +154,12 @@ def test_warp_features(lib):
     (2, 3, 16, 9, 11, 2, (96, 64), True),
 ])
 def test_mlp_forward(lib, B, K, C, H, W, D, hidden, per_pixel):
-    lib.srcv_set_variant(N.VARIANT_AUTO)
+    lib.srcv_set_variant(N.VARIANT_GENERIC)         # the fp32 SIMT variant (the hero layout would pick tcgen05)
     t = make_tuple(B, K, H, W, channels=C, seed=21)
     wts = _weights(K, C, hidden)
     planes = (0.3 + 4.0 * torch.rand(B, D, H, W, generator=torch.Generator().manual_seed(22))) if per_pixel else None
     cost, lowest, planes_bd, mask, used = emu.mlp_forward(t, D, wts, planes=planes)
+    lib.srcv_set_variant(N.VARIANT_AUTO)
     assert used == "mlp_generic_fp32"
     oc, ol, op, om = O.forward_mlp(**t, weights=tuple(wts), num_depth_bins=D, depth_planes_bdhw=planes,
                                    return_mask=True)
@@ -189,6 +193,51 @@ def test_mlp_backward(lib, B, K, C, H, W, D, hidden, per_pixel, sms):
     for name, o, r in zip(("cur", "src", "w1", "b1", "w2", "b2", "w3", "b3"), ours, ref):
         assert o.shape == r.shape
         assert _rel(o, r) < 2e-5, f"grad {name}: rel err {_rel(o, r):.2e}"
+
+
+# ----------------------------------------------------------------------------------------- #
+# tcgen05 kernel against the functional TMEM / MMA / mbarrier model (tests/emu/emu_tc.h)       #
+# ----------------------------------------------------------------------------------------- #
+def test_tc_selftest_three_product_gemm(lib):
+    """srcv_tc_selftest_f32: D = A W^T through tcgen05.mma with the (hi, lo) fp16 split."""
+    g = torch.Generator().manual_seed(0)
+    for Kp, scale in ((64, 0.1), (208, 1.0)):
+        A, Wm = torch.randn(128, Kp, generator=g), scale * torch.randn(128, Kp, generator=g)
+        Dm = torch.full((128, 128), float("nan"))
+        scratch = torch.zeros(2 * 128 * Kp * 2 + 256, dtype=torch.uint8)
+        assert lib.srcv_tc_selftest_f32(emu._p(A), emu._p(Wm), Kp, emu._p(Dm), emu._p(scratch), None) == 0
+        ref = A.double() @ Wm.double().T
+        assert (Dm.double() - ref).abs().max().item() <= 4e-6 * ref.abs().max().item()
+    assert lib.srcv_tc_selftest_f32(emu._p(A), emu._p(Wm), 40, emu._p(Dm), emu._p(scratch), None) != 0   # Kp % 16
+
+
+@pytest.mark.parametrize("B,H,W,D,per_pixel,sms", [
+    (1, 8, 16, 8, False, 2),      # 8 tiles over 2 persistent CTAs: the steady-state pipeline (prologue, overlap, drain)
+    (2, 5, 19, 6, False, 3),      # ragged patches (partial 16x2 tiles), D not a multiple of the 4-plane tile, 2 frames
+    (1, 6, 16, 4, True, 8),       # per-pixel planes; more CTAs than tiles per CTA > 1
+])
+def test_mlp_forward_tcgen05(lib, B, H, W, D, per_pixel, sms):
+    """mlp_tc_kernel (K = 7, C = 16, 128/128): 640 host threads per CTA run the real worker / MMA-warp
+    code; TMEM, tcgen05.mma (executed at commit), mbarriers and the bulk copy are the functional
+    model.  Checks the protocol (no deadlock, no lost tile) and the arithmetic against the oracle."""
+    lib.emu_set_sms(sms)
+    lib.srcv_set_variant(N.VARIANT_AUTO)
+    K, C_ = 7, 16
+    t = make_tuple(B, K, H, W, channels=C_, seed=51)
+    wts = _weights(K, C_)
+    planes = (0.3 + 4.0 * torch.rand(B, D, H, W, generator=torch.Generator().manual_seed(52))) if per_pixel else None
+    cost, lowest, planes_bd, mask, used = emu.mlp_forward(t, D, wts, planes=planes)
+    assert used == "mlp_tc_tcgen05_f16x3"
+    oc, ol, op, om = O.forward_mlp(**t, weights=tuple(wts), num_depth_bins=D, depth_planes_bdhw=planes,
+                                   return_mask=True)
+    assert_cost_close("mlp", cost, oc, what="emu tcgen05")
+    assert_lowest_close("mlp", lowest, planes if per_pixel else planes_bd.view(B, D, 1, 1), oc, what="emu tcgen05")
+    assert_mask_close(mask, om, what="emu tcgen05")
+    # the fp32 SIMT variant of the same call agrees to the split's 2^-21
+    lib.srcv_set_variant(N.VARIANT_GENERIC)
+    cost_g, *_ = emu.mlp_forward(t, D, wts, planes=planes)
+    lib.srcv_set_variant(N.VARIANT_AUTO)
+    assert (cost - cost_g).abs().max().item() <= 2e-5 * oc.abs().max().item() + 1e-6
 
 
 # ----------------------------------------------------------------------------------------- #
