@@ -45,7 +45,12 @@ __device__ void view_params(const float* __restrict__ Kmat, const float* __restr
     Hm[0][j] -= cxo * Hm[2][j];
     Hm[1][j] -= cyo * Hm[2][j];
   }
-  const double tx = P[0][3] - cxo * P[2][3], ty = P[1][3] - cyo * P[2][3], tz = P[2][3];
+  // The reference divides by z' = z + eps (utils/geometry_utils.py:83-87):
+  //   x / z' - cxo = (x - cxo z - cxo eps) / z',
+  // so the centred numerator also carries -cxo eps.  Irrelevant at metric depths (3e-6 px at
+  // z = 0.25 m) but 5e-5 px at z = 1 mm: found by the fuzzer on the host emulation.
+  const double tx = P[0][3] - cxo * P[2][3] - cxo * (double)kEpsProj,
+               ty = P[1][3] - cyo * P[2][3] - cyo * (double)kEpsProj, tz = P[2][3];
   // centre the INPUT: p = (W/2 + dx, H/2 + dy, 1)
   const double ux = 0.5 * (double)W, uy = 0.5 * (double)H;
 #pragma unroll

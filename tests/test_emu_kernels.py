@@ -103,6 +103,24 @@ def test_dot_forward(lib, B, K, C, H, W, D, sms, variant, expect):
     assert torch.equal(torch.gather(planes_bd.view(B, D, 1, 1).expand_as(cost), 1, idx).squeeze(1), lowest)
 
 
+def test_dot_millimetre_depths_keep_the_reference_epsilon(lib):
+    """Regression for a fuzzer finding: the reference divides by z' = z + 1e-8
+    (utils/geometry_utils.py:83-87); in centred coordinates the numerator must carry -cxo*eps as
+    well, otherwise the sample position is off by cxo*eps/z — 5e-5 px at z = 1 mm.  Judged
+    against the fp64 evaluation like tests/parity.py."""
+    lib.emu_set_sms(4)
+    lib.srcv_set_variant(N.VARIANT_AUTO)
+    B, K, C_, H, W, D = 2, 4, 16, 6, 22, 4
+    t = make_tuple(B, K, H, W, channels=C_, seed=77, t_range=(0.0, 0.0), max_angle=0.6)   # pure rotations
+    t["min_depth"], t["max_depth"] = torch.full((1, 1, 1, 1), 1e-3), torch.full((1, 1, 1, 1), 1e-2)
+    cost, _, _, used = emu.dot_forward(t, D)
+    oc, *_ = O.forward_dot(**t, num_depth_bins=D)
+    o64, *_ = O.forward_dot(**{k: v.double() for k, v in t.items()}, num_depth_bins=D)
+    e_ref = (oc.double() - o64).abs().max().item()
+    e_ours = (cost.double() - o64).abs().max().item()
+    assert e_ours <= 2 * e_ref + 1e-6 * o64.abs().max().item(), (e_ours, e_ref, used)
+
+
 @pytest.mark.parametrize("C,sms", [(8, 4), (16, 4), (16, 148)])
 def test_dot_forward_per_pixel_planes(lib, C, sms):
     lib.emu_set_sms(sms)
