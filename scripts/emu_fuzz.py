@@ -2,7 +2,7 @@
 random shapes, camera tuples (incl. views looking away, huge / tiny depths, planes behind the
 source cameras, out-of-frustum projections), plane modes and variants.  CPU only.
 
-    python scripts/emu_fuzz.py [--cases 200] [--seed 0] [--kinds dot,mlp,dotbwd,mlpbwd]
+    python scripts/emu_fuzz.py [--cases 200] [--seed 0] [--kinds dot,mlp,dotbwd,mlpbwd,tc]
 """
 import argparse
 import math
@@ -23,7 +23,11 @@ from tests.parity import cost_tol  # noqa: E402
 def rand_case(g, kind):
     ri = lambda a, b: int(torch.randint(a, b + 1, (1,), generator=g))
     B, K = ri(1, 2), ri(1, 8 if kind.startswith("dot") else 7)
+    if kind == "tc":                        # the tcgen05 kernel's layout
+        K = 7
     C = [8, 16, 16, 16, 12][ri(0, 4)] if kind == "dot" else ([8, 16, 16][ri(0, 2)])
+    if kind == "tc":
+        C = 16
     if kind == "dotbwd":
         C = [8, 16, 32][ri(0, 2)]
     H, W, D = ri(3, 14), ri(4, 24), ri(1, 9)
@@ -62,8 +66,11 @@ def run(kind, g, lib):
             extra = f" | vs fp64: ours {e_ours:.2e}, reference-fp32 {e_ref:.2e}"
             ok = bool(torch.isfinite(cost).all()) and e_ours <= 2 * e_ref + 1e-6 * o64.abs().max().item()
         return ok, f"{used} {B,K,C,H,W,D} err {err:.2e} tol {tol:.2e}{extra}"
-    if kind == "mlp":
+    if kind in ("mlp", "tc"):
         hidden = [(128, 128), (64, 96), (128, 32)][int(torch.randint(0, 3, (1,), generator=g))]
+        if kind == "tc":
+            hidden = (128, 128)
+            lib.srcv_set_variant(N.VARIANT_AUTO)
         sd = mlp_state(views=K, channels=C, hidden=hidden, seed=1)
         wts = [sd[f"mlp.net.{i}.{n}"] for i in (0, 2, 4) for n in ("weight", "bias")]
         cost, lowest, pbd, mask, used = emu.mlp_forward(t, D, wts, planes=planes)
