@@ -8,12 +8,13 @@ tests/test_emu_python_stack.py (host emulation); this file is its run on real ha
 first execution is the round-end GPU tier.)
 
 Tolerance: gradients are fp32 sums of up to D*H*W*K atomically accumulated terms; the order
-differs between runs and from the CPU: rel. 1e-4 of the largest reference entry.  LeakyReLU has a
-kink at 0: a pre-activation of ~1e-7 takes either sign depending on the fp32 summation order
-(scripts/emu_fuzz.py sees it in a few percent of random cases, on either side, each time matching
-the fp64 gradients everywhere else), which perturbs a bounded set of entries by up to ~1e-2 of the
-maximum.  Such a case passes if the relative L2 error stays below 5e-3 — an indexing or protocol
-bug does not."""
+differs between runs and from the CPU: rel. 1e-4 of the largest entry of the fp64 oracle gradient.
+Why fp64: LeakyReLU has a kink at 0 and a pre-activation of ~1e-7 takes either sign depending on
+the fp32 summation order.  scripts/emu_fuzz.py sees it in ~8 % of random cases — almost always on
+the side of the fp32 composite (the reference's own arithmetic) while the kernel matches the fp64
+gradients on every entry; rarely on the kernel's side, where a bounded set of entries moves by up to
+~1e-2 of the maximum.  That rare case passes if the relative L2 error stays below 2e-2; an
+indexing or protocol bug does not."""
 import pytest
 import torch
 
@@ -29,15 +30,15 @@ RTOL = 1e-4
 
 
 def _rel(a, b):
-    a, b = a.detach().cpu(), b.detach().cpu()
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
     return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
 
 
 def _grad_close(a, b):
-    a, b = a.detach().cpu(), b.detach().cpu()
     if _rel(a, b) < RTOL:
         return True
-    return ((a - b).norm() / (b.norm() + 1e-30)).item() < 5e-3      # LeakyReLU kink flip, see the docstring
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item() < 2e-2      # LeakyReLU kink flip on our side, see the docstring
 
 
 def _manager(K, C, H, W, D, hidden=(128, 128), fast=False):
@@ -47,13 +48,16 @@ def _manager(K, C, H, W, D, hidden=(128, 128), fast=False):
     return m.cuda().train()
 
 
-def _oracle_grads(t, wts, D, gcost, planes):
-    tc = dict(t)
-    tc["cur_feats"] = t["cur_feats"].clone().requires_grad_(True)
-    tc["src_feats"] = t["src_feats"].clone().requires_grad_(True)
-    wo = [w.detach().cpu().clone().requires_grad_(True) for w in wts]
-    oc, *_ = O.forward_mlp(**tc, weights=tuple(wo), num_depth_bins=D, depth_planes_bdhw=planes)
-    (oc * gcost).sum().backward()
+def _oracle_grads(t, wts, D, gcost, planes, dtype=torch.float64):
+    """Autograd through the oracle in fp64 (see the module docstring: the fp32 composite — the
+    reference's own arithmetic — flips LeakyReLU kinks more often than the kernel does)."""
+    tc = {k: (v.to(dtype) if torch.is_tensor(v) else v) for k, v in t.items()}
+    tc["cur_feats"] = tc["cur_feats"].clone().requires_grad_(True)
+    tc["src_feats"] = tc["src_feats"].clone().requires_grad_(True)
+    wo = [w.detach().cpu().to(dtype).clone().requires_grad_(True) for w in wts]
+    oc, *_ = O.forward_mlp(**tc, weights=tuple(wo), num_depth_bins=D,
+                           depth_planes_bdhw=None if planes is None else planes.to(dtype))
+    (oc * gcost.to(dtype)).sum().backward()
     return oc.detach(), [tc["cur_feats"].grad, tc["src_feats"].grad] + [w.grad for w in wo]
 
 
@@ -78,8 +82,10 @@ def test_hero_training_matches_oracle_autograd(cuda_device, B, K, C, H, W, D, hi
     torch.cuda.synchronize()
     assert _native.last_variant() == "mlp_backward_fp32_recompute"
     params = [p for i in (0, 2, 4) for p in (m.mlp.net[i].weight, m.mlp.net[i].bias)]
-    oc, ref = _oracle_grads(t, params, D, gcost, planes)
-    assert_cost_close("mlp", cost, oc, what="hero training forward")
+    oc64, ref = _oracle_grads(t, params, D, gcost, planes)
+    oc, *_ = O.forward_mlp(**t, weights=tuple(p.detach().cpu() for p in params), num_depth_bins=D,
+                           depth_planes_bdhw=planes)
+    assert_cost_close("mlp", cost, oc, oc64, what="hero training forward")
     ours = [d["cur_feats"].grad, d["src_feats"].grad] + [p.grad for p in params]
     for name, o, r in zip(("cur", "src", "w1", "b1", "w2", "b2", "w3", "b3"), ours, ref):
         assert o is not None and tuple(o.shape) == tuple(r.shape), name
