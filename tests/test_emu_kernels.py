@@ -200,17 +200,21 @@ def test_mlp_backward(lib, B, K, C, H, W, D, hidden, per_pixel, sms):
     g = torch.Generator().manual_seed(4)
     gcost = torch.randn(B, D, H, W, generator=g)
     planes = (0.3 + 4.0 * torch.rand(B, D, H, W, generator=g)) if per_pixel else None
-    tc = dict(t)
-    tc["cur_feats"] = t["cur_feats"].clone().requires_grad_(True)
-    tc["src_feats"] = t["src_feats"].clone().requires_grad_(True)
-    wo = [w.clone().requires_grad_(True) for w in wts]
-    oc, _, op, _ = O.forward_mlp(**tc, weights=tuple(wo), num_depth_bins=D, depth_planes_bdhw=planes)
-    (oc * gcost).sum().backward()
+    # fp64 oracle gradients: the fp32 composite flips LeakyReLU kinks (a ~1e-7 pre-activation) more
+    # often than the kernel does, see scripts/emu_fuzz.py
+    tc = {k: v.double() for k, v in t.items()}
+    tc["cur_feats"] = tc["cur_feats"].clone().requires_grad_(True)
+    tc["src_feats"] = tc["src_feats"].clone().requires_grad_(True)
+    wo = [w.double().clone().requires_grad_(True) for w in wts]
+    oc, _, op, _ = O.forward_mlp(**tc, weights=tuple(wo), num_depth_bins=D,
+                                 depth_planes_bdhw=None if planes is None else planes.double())
+    (oc * gcost.double()).sum().backward()
     ref = [tc["cur_feats"].grad, tc["src_feats"].grad] + [w.grad for w in wo]
+    op = op.float()
     ours = emu.mlp_backward(t, D, wts, gcost, planes=planes if per_pixel else op[:, :, 0, 0].detach())
     for name, o, r in zip(("cur", "src", "w1", "b1", "w2", "b2", "w3", "b3"), ours, ref):
         assert o.shape == r.shape
-        assert _rel(o, r) < 2e-5, f"grad {name}: rel err {_rel(o, r):.2e}"
+        assert _rel(o.double(), r) < 2e-5, f"grad {name}: rel err {_rel(o.double(), r):.2e}"
 
 
 # ----------------------------------------------------------------------------------------- #
