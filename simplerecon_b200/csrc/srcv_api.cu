@@ -13,7 +13,7 @@ namespace srcv {
 
 static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_variant{SRCV_VARIANT_AUTO};
-static const char* g_last_variant = "none";
+static std::atomic<const char*> g_last_variant{"none"};   // process-global, like g_variant
 static thread_local char g_err[512] = "";
 
 void note_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
@@ -135,7 +135,7 @@ int32_t srcv_set_variant(int32_t v) {
   return SRCV_OK;
 }
 
-const char* srcv_last_variant(void) { return g_last_variant; }
+const char* srcv_last_variant(void) { return g_last_variant.load(); }
 
 uint64_t srcv_launch_count(void) { return g_launches.load(); }
 
@@ -165,13 +165,13 @@ int32_t srcv_dot_forward_f32(const srcv_shape* s, const float* cur, const float*
   const bool per_pixel = pl->mode == SRCV_PLANES_PER_PIXEL;
   const float* planes = pl->mode == SRCV_PLANES_FROM_RANGE ? ws.planes : pl->planes;
   if (fast) {
-    g_last_variant = "dot_fast_c4planar";
+    g_last_variant.store("dot_fast_c4planar");
     err = launch_dot_fast(*s, cur, ws, planes, per_pixel, cost, lowest, stream);
   } else {
-    g_last_variant = "dot_generic";
+    g_last_variant.store("dot_generic");
     err = launch_dot_generic(*s, cur, src, ws, planes, per_pixel, cost, lowest, stream);
   }
-  if (err != cudaSuccess) return cuda_fail(err, g_last_variant);
+  if (err != cudaSuccess) return cuda_fail(err, g_last_variant.load());
   if (pr) cudaEventRecord(pr->e[2], stream);
   return SRCV_OK;
 }
@@ -199,9 +199,9 @@ int32_t srcv_dot_backward_f32(const srcv_shape* s, const float* cur, const float
   if (err != cudaSuccess) return cuda_fail(err, "memset grad_src");
   const bool per_pixel = pl->mode == SRCV_PLANES_PER_PIXEL;
   const float* planes = pl->mode == SRCV_PLANES_FROM_RANGE ? ws.planes : pl->planes;
-  g_last_variant = "dot_backward_atomic";
+  g_last_variant.store("dot_backward_atomic");
   err = launch_dot_backward(*s, cur, src, ws, planes, per_pixel, grad_cost, grad_cur, grad_src, stream);
-  if (err != cudaSuccess) return cuda_fail(err, g_last_variant);
+  if (err != cudaSuccess) return cuda_fail(err, g_last_variant.load());
   return SRCV_OK;
 }
 
@@ -228,9 +228,9 @@ int32_t srcv_warp_features_f32(const srcv_shape* s, const float* src, const srcv
   pl.planes = depth_plane;
   cudaError_t err = launch_prep(*s, *cams, pl, src, nullptr, ws, false, stream);
   if (err != cudaSuccess) return cuda_fail(err, "prep");
-  g_last_variant = "warp_plane";
+  g_last_variant.store("warp_plane");
   err = launch_warp_plane(*s, src, ws, depth_plane, per_pixel != 0, warped, depths, mask, stream);
-  if (err != cudaSuccess) return cuda_fail(err, g_last_variant);
+  if (err != cudaSuccess) return cuda_fail(err, g_last_variant.load());
   return SRCV_OK;
 }
 
@@ -287,13 +287,13 @@ int32_t srcv_mlp_forward_f32(const srcv_shape* s, const float* cur, const float*
   const bool per_pixel = pl->mode == SRCV_PLANES_PER_PIXEL;
   const float* planes = pl->mode == SRCV_PLANES_FROM_RANGE ? ws.planes : pl->planes;
   if (tc) {
-    g_last_variant = "mlp_tc_tcgen05_f16x3";
+    g_last_variant.store("mlp_tc_tcgen05_f16x3");
     err = launch_mlp_tc(*s, cur, ws, planes, per_pixel, *w, cost, lowest, overall_mask, stream);
   } else {
-    g_last_variant = "mlp_generic_fp32";
+    g_last_variant.store("mlp_generic_fp32");
     err = launch_mlp_generic(*s, cur, src, ws, planes, per_pixel, *w, cost, lowest, overall_mask, stream);
   }
-  if (err != cudaSuccess) return cuda_fail(err, g_last_variant);
+  if (err != cudaSuccess) return cuda_fail(err, g_last_variant.load());
   if (pr) cudaEventRecord(pr->e[2], stream);
   return SRCV_OK;
 }
@@ -336,9 +336,9 @@ int32_t srcv_mlp_backward_f32(const srcv_shape* s, const float* cur, const float
   }
   const bool per_pixel = pl->mode == SRCV_PLANES_PER_PIXEL;
   const float* planes = pl->mode == SRCV_PLANES_FROM_RANGE ? ws.planes : pl->planes;
-  g_last_variant = "mlp_backward_fp32_recompute";
+  g_last_variant.store("mlp_backward_fp32_recompute");
   err = launch_mlp_backward(*s, cur, src, ws, planes, per_pixel, *w, grad_cost, grad_cur, grad_src, *g, stream);
-  if (err != cudaSuccess) return cuda_fail(err, g_last_variant);
+  if (err != cudaSuccess) return cuda_fail(err, g_last_variant.load());
   return SRCV_OK;
 }
 
