@@ -27,7 +27,7 @@ from tests.parity import (assert_cost_close, assert_lowest_close, assert_mask_cl
 
 @pytest.fixture(scope="module")
 def lib():
-    lib = emu.load()
+    lib = emu.load_or_skip()
     yield lib
     lib.emu_set_sms(4)
     lib.srcv_set_variant(N.VARIANT_AUTO)

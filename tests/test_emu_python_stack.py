@@ -22,7 +22,7 @@ from tests.parity import assert_cost_close, assert_lowest_close, assert_mask_clo
 
 @pytest.fixture()
 def emulated(monkeypatch):
-    lib = emu.load()
+    lib = emu.load_or_skip()
     lib.emu_set_sms(4)
     lib.srcv_set_variant(_native.VARIANT_AUTO)
     monkeypatch.setattr(_native, "_lib", lib)
