@@ -262,6 +262,24 @@ def test_mlp_forward_tcgen05(lib, B, H, W, D, per_pixel, sms):
     assert (cost - cost_g).abs().max().item() <= 2e-5 * oc.abs().max().item() + 1e-6
 
 
+def test_forward_sweeps_are_deterministic(lib):
+    """The forward kernels have no order-dependent arithmetic (the split dot sweep reduces through
+    the last-arriver, the hero kernel reduces its four quarters in a fixed order): two runs with
+    differently interleaved host threads must agree bit for bit."""
+    lib.emu_set_sms(148)
+    lib.srcv_set_variant(N.VARIANT_AUTO)
+    t = make_tuple(1, 7, 8, 16, channels=16, seed=61)
+    a = emu.dot_forward(t, 16)
+    b = emu.dot_forward(t, 16)
+    assert a[3] == "dot_fast_c4planar" and torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    lib.emu_set_sms(3)
+    wts = _weights(7, 16)
+    a = emu.mlp_forward(t, 8, wts)
+    b = emu.mlp_forward(t, 8, wts)
+    assert a[4] == "mlp_tc_tcgen05_f16x3"
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[3], b[3])
+
+
 # ----------------------------------------------------------------------------------------- #
 # C-ABI argument validation (srcv_api.cu) — runs the real front end, no kernel is launched    #
 # ----------------------------------------------------------------------------------------- #
