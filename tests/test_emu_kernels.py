@@ -262,6 +262,39 @@ def test_mlp_forward_tcgen05(lib, B, H, W, D, per_pixel, sms):
     assert (cost - cost_g).abs().max().item() <= 2e-5 * oc.abs().max().item() + 1e-6
 
 
+def test_dot_forward_compile_time_map_size(lib):
+    """The 160x120 instantiation of the fast dot sweep (compile-time tap offsets) — the kernel the
+    BASELINE configs run — on one full-size frame with few planes."""
+    lib.emu_set_sms(4)
+    lib.srcv_set_variant(N.VARIANT_AUTO)
+    B, K, C_, H, W, D = 1, 2, 16, 120, 160, 8
+    t = make_tuple(B, K, H, W, channels=C_, seed=91)
+    cost, lowest, planes_bd, used = emu.dot_forward(t, D)
+    assert used == "dot_fast_c4planar"
+    oc, *_ = O.forward_dot(**t, num_depth_bins=D)
+    assert_cost_close("dot", cost, oc, what="emu dot 160x120")
+    assert_lowest_close("dot", lowest, planes_bd.view(B, D, 1, 1), oc, what="emu dot 160x120")
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("SRCV_EMU_SLOW"), reason="several minutes: set SRCV_EMU_SLOW=1")
+def test_mlp_forward_tcgen05_compile_time_map_size(lib):
+    """The 160x120 instantiation of the tcgen05 kernel on one full-size frame, one plane chunk
+    (600 tiles through the 640-thread pipeline)."""
+    lib.emu_set_sms(8)
+    lib.srcv_set_variant(N.VARIANT_AUTO)
+    B, K, C_, H, W, D = 1, 7, 16, 120, 160, 4
+    t = make_tuple(B, K, H, W, channels=C_, seed=92)
+    wts = _weights(K, C_)
+    cost, lowest, planes_bd, mask, used = emu.mlp_forward(t, D, wts)
+    assert used == "mlp_tc_tcgen05_f16x3"
+    oc, ol, op, om = O.forward_mlp(**t, weights=tuple(wts), num_depth_bins=D, return_mask=True)
+    o64, *_ = O.forward_mlp(**{k: v.double() for k, v in t.items()}, weights=tuple(w.double() for w in wts),
+                            num_depth_bins=D)
+    # at 160-pixel coordinates the reference's own fp32 run is ~1.5e-5 off its fp64 evaluation
+    assert_cost_close("mlp", cost, oc, o64, what="emu tcgen05 160x120")
+    assert_mask_close(mask, om, what="emu tcgen05 160x120")
+
+
 def test_forward_sweeps_are_deterministic(lib):
     """The forward kernels have no order-dependent arithmetic (the split dot sweep reduces through
     the last-arriver, the hero kernel reduces its four quarters in a fixed order): two runs with
