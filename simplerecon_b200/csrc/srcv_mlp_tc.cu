@@ -271,10 +271,21 @@ struct TileCoord { int b, d0, x0, y0; };
 __device__ __forceinline__ TileCoord tile_coord(long long id, int D, int tiles_x, int tiles_xy) {
   TileCoord t;
   const int nd = (D + kTileD - 1) / kTileD;
+#ifdef SRCV_TC_TILE32
+  // Round-2 experiment (off by default): tile ids fit 32 bits for every supported shape (the
+  // launcher refuses >= 2^31 tiles), and the 64-bit div/mod pairs cost ~120 instructions per
+  // thread and tile (two make_tile_row per tile) — 7 % of the worker's instruction budget.
+  const unsigned uid = (unsigned)id, und = (unsigned)nd, uxy = (unsigned)tiles_xy;
+  t.d0 = (int)(uid % und) * kTileD;
+  const unsigned r = uid / und;
+  const int txy = (int)(r % uxy);
+  t.b = (int)(r / uxy);
+#else
   t.d0 = (int)(id % nd) * kTileD;
   const long long r = id / nd;
   const int txy = (int)(r % tiles_xy);
   t.b = (int)(r / tiles_xy);
+#endif
   t.x0 = (txy % tiles_x) * kTileW;
   t.y0 = (txy / tiles_x) * kTileH;
   return t;
@@ -668,6 +679,7 @@ cudaError_t launch_mlp_tc(const srcv_shape& s, const float* cur, const Workspace
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles_x = (s.W + kTileW - 1) / kTileW, tiles_y = (s.H + kTileH - 1) / kTileH;
   const long long num_tiles = (long long)s.B * ((s.D + kTileD - 1) / kTileD) * tiles_x * tiles_y;
+  if (num_tiles >= (1ll << 31)) return cudaErrorInvalidValue;   // tile ids are kept 32-bit-safe
   const int grid = (int)(num_tiles < sms ? num_tiles : sms);
   const float4* src4 = reinterpret_cast<const float4*>(ws.src_c4);
   const float4* cur4 = reinterpret_cast<const float4*>(ws.cur_c4);
