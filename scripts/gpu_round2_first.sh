@@ -2,7 +2,7 @@
 # First GPU call of the next round (run through gpurun, one GPU): everything that was written
 # after round 1's GPU budget was spent, in one box acquisition.  Every step has its own timeout;
 # logs land in gpurun_out/r02_first_*.  Build the experiment library BEFORE calling gpurun:
-#   python -m simplerecon_b200.build --out simplerecon_b200/lib/libsrcv_b200_uw.so --extra=-DSRCV_TC_UNIFORM_WARP --extra=-DSRCV_TC_EARLY_FLAGS --extra=-DSRCV_TC_TILE32
+#   python -m simplerecon_b200.build --out simplerecon_b200/lib/libsrcv_b200_uw.so --extra=-DSRCV_TC_UNIFORM_WARP --extra=-DSRCV_TC_EARLY_FLAGS --extra=-DSRCV_TC_TILE32 --extra=-DSRCV_TC_CLAMPED_TAPS
 #   gpurun --timeout 900 -- 'bash scripts/gpu_round2_first.sh'
 set -u
 O=gpurun_out

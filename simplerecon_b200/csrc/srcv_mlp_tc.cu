@@ -192,6 +192,11 @@ __device__ __forceinline__ unsigned view_block(const RowCtx& rc, const ViewParam
   // reference modules/cost_volume.py:590-623); padding taps contribute zeros
   // two taps (8 vector loads) in flight at a time keeps the worker inside its register budget
   const bool interior = __all_sync(0xffffffffu, tp.valid == 15u);
+#ifdef SRCV_TC_CLAMPED_TAPS
+  const int cxa = min(max(tp.x0, 0), W - 1), cxb = min(max(tp.x0 + 1, 0), W - 1);
+  const int cya = min(max(tp.y0, 0), H - 1) * W, cyb = min(max(tp.y0 + 1, 0), H - 1) * W;
+  const int coff[4] = {cya + cxa, cya + cxb, cyb + cxa, cyb + cxb};
+#endif
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     float4 f[2][4];
@@ -201,8 +206,20 @@ __device__ __forceinline__ unsigned view_block(const RowCtx& rc, const ViewParam
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (interior) f[tt][j] = __ldg(q + off[tap] + (size_t)j * HW);
+#ifdef SRCV_TC_CLAMPED_TAPS
+        else {
+          // Round-2 experiment (off by default): branch-free borders.  Every tap is loaded from an
+          // in-range (clamped) texel and padding taps are zeroed by selects on the VALUES (not on
+          // the weights: a non-finite texel must not leak through 0 * inf) — instead of a
+          // BSSY / BRA / CS2R region around every conditional load.
+          const float4 tv = __ldg(view4 + coff[tap] + (size_t)j * HW);
+          const bool on = ((tp.valid >> tap) & 1u) != 0u;
+          f[tt][j] = make_float4(on ? tv.x : 0.f, on ? tv.y : 0.f, on ? tv.z : 0.f, on ? tv.w : 0.f);
+        }
+#else
         else f[tt][j] = ((tp.valid >> tap) & 1u) ? __ldg(q + off[tap] + (size_t)j * HW)
                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+#endif
       }
     }
     const float wa = wgt[2 * half], wb = wgt[2 * half + 1];
