@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SRCV_ABI_VERSION 1
+#define SRCV_ABI_VERSION 2
 
 typedef enum srcv_status {
   SRCV_OK = 0,
@@ -76,6 +76,10 @@ typedef struct srcv_planes {
   const float* max_depth;  /* device scalar, FROM_RANGE only                 */
   const float* ramp;       /* device (D), FROM_RANGE only                    */
   float* planes_out;       /* device (B,D), FROM_RANGE only (may be NULL)    */
+  int32_t range_per_frame; /* FROM_RANGE: 0 = min/max_depth are single scalars (the
+                            * (1,1,1,1) tensors of depth_model.py:358-359); 1 = B values each,
+                            * one range per frame (generate_depth_planes broadcasts a
+                            * (B,1,1,1) range, modules/cost_volume.py:124-127)  */
 } srcv_planes;
 
 /* Camera block shared by both volumes (all DEVICE pointers). */
@@ -95,6 +99,11 @@ typedef struct srcv_mlp_weights {
   const float* w3; const float* b3; /* (1,H2), (1)                            */
   int32_t hidden1;                  /* H1                                     */
   int32_t hidden2;                  /* H2                                     */
+  /* Optional: DEVICE image written by srcv_mlp_pack_weights for exactly these weights
+   * (srcv_mlp_packed_bytes bytes, 256-byte aligned).  NULL = the forward call packs the
+   * weights itself, into its workspace, on every call.  A caller whose parameters change
+   * rarely (inference; one optimiser step per forward in training) packs once per change.  */
+  const void* packed_image;
 } srcv_mlp_weights;
 
 /* ---- library / device ------------------------------------------------- */
@@ -131,6 +140,9 @@ int32_t srcv_dot_forward_f32(const srcv_shape* shape,
  *   grad_cur (B,C,H,W) out      grad_src (B,K,C,H,W) out (zeroed here, then accumulated
  *   with float atomics: reproducible to fp32 rounding, not bit-for-bit)           */
 size_t srcv_dot_backward_workspace_bytes(const srcv_shape* shape);
+/* 1 if srcv_dot_backward_f32 serves this shape (C in {8,16,32}), else 0 — lets the caller
+ * refuse an unsupported training shape in forward() instead of at backward() time.          */
+int32_t srcv_dot_backward_supported(const srcv_shape* shape);
 int32_t srcv_dot_backward_f32(const srcv_shape* shape, const float* cur_feats, const float* src_feats,
                               const srcv_cameras* cams, const srcv_planes* planes,
                               const float* grad_cost, float* grad_cur, float* grad_src,
@@ -160,6 +172,12 @@ int32_t srcv_warp_features_f32(const srcv_shape* shape, const float* src_feats,
  *   overall_mask (B,H,W) uint8 out (1 = some source view sees the pixel at the
  *   LAST plane, :625-637); NULL when return_mask is False.                   */
 size_t srcv_mlp_workspace_bytes(const srcv_shape* shape, const srcv_mlp_weights* w);
+/* Size of the packed weight image of the tensor-core variant for this shape / these widths
+ * (0 when that variant does not serve them and there is nothing to pack), and the packing
+ * itself: `image` DEVICE, 256-byte aligned, srcv_mlp_packed_bytes bytes.                   */
+size_t srcv_mlp_packed_bytes(const srcv_shape* shape, const srcv_mlp_weights* w);
+int32_t srcv_mlp_pack_weights(const srcv_shape* shape, const srcv_mlp_weights* w, void* image,
+                              void* stream);
 int32_t srcv_mlp_forward_f32(const srcv_shape* shape,
                              const float* cur_feats, const float* src_feats,
                              const srcv_cameras* cams, const srcv_planes* planes,
@@ -185,6 +203,8 @@ typedef struct srcv_mlp_grads {
   float* w3; float* b3;
 } srcv_mlp_grads;
 size_t srcv_mlp_backward_workspace_bytes(const srcv_shape* shape, const srcv_mlp_weights* w);
+/* 1 if srcv_mlp_backward_f32 serves this shape and these hidden widths, else 0.             */
+int32_t srcv_mlp_backward_supported(const srcv_shape* shape, int32_t hidden1, int32_t hidden2);
 int32_t srcv_mlp_backward_f32(const srcv_shape* shape,
                               const float* cur_feats, const float* src_feats,
                               const srcv_cameras* cams, const srcv_planes* planes,

@@ -41,3 +41,12 @@ else
   echo "build it first: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/probes/l1_gather_probe scripts/probes/l1_gather_probe.cu"
 fi
 ls -la $O | tail -n 12
+echo "== 7. ncu: hero kernel, variant build (all four switches), full sections + source"
+if [ -f $UW ]; then
+  SRCV_B200_LIB=$UW timeout 300 ncu --set full --clock-control none --import-source on -k regex:mlp_tc_kernel -s 1 -c 1 \
+      -o $O/prof_r02_hero_uw python scripts/run_once.py cfg2 4 2 > $O/r02_first_ncu_hero_uw.log 2>&1; echo "ncu rc=$?"
+fi
+echo "== 8. dot bench (cfg1) + stress cfgS on the default build"
+timeout 200 python bench.py --workload cfg1 --steps 20 --warmup 3 --no-cpu-baseline 2>$O/r02_first_cfg1.err | tail -n 1 > $O/r02_first_cfg1.json
+timeout 300 python bench.py --workload stress_dot --steps 5 --warmup 3 --no-cpu-baseline 2>$O/r02_first_stress_dot.err | tail -n 1 > $O/r02_first_stress_dot.json; cat $O/r02_first_stress_dot.json | head -c 600
+ls -la $O | tail -n 14

@@ -36,7 +36,7 @@ class Shape(C.Structure):
 
 class Planes(C.Structure):
     _fields_ = [("mode", C.c_int32), ("planes", _fp), ("min_depth", _fp), ("max_depth", _fp),
-                ("ramp", _fp), ("planes_out", _fp)]
+                ("ramp", _fp), ("planes_out", _fp), ("range_per_frame", C.c_int32)]
 
 
 class Cameras(C.Structure):
@@ -45,7 +45,7 @@ class Cameras(C.Structure):
 
 class MlpWeights(C.Structure):
     _fields_ = [("w1", _fp), ("b1", _fp), ("w2", _fp), ("b2", _fp), ("w3", _fp), ("b3", _fp),
-                ("hidden1", C.c_int32), ("hidden2", C.c_int32)]
+                ("hidden1", C.c_int32), ("hidden2", C.c_int32), ("packed_image", _fp)]
 
 
 class MlpGrads(C.Structure):
@@ -62,16 +62,20 @@ SYMBOLS = {
     "srcv_dot_forward_f32": (C.c_int32, [C.POINTER(Shape), _fp, _fp, C.POINTER(Cameras),
                                          C.POINTER(Planes), _fp, _fp, _fp, C.c_size_t, _fp]),
     "srcv_dot_backward_workspace_bytes": (C.c_size_t, [C.POINTER(Shape)]),
+    "srcv_dot_backward_supported": (C.c_int32, [C.POINTER(Shape)]),
     "srcv_dot_backward_f32": (C.c_int32, [C.POINTER(Shape), _fp, _fp, C.POINTER(Cameras), C.POINTER(Planes),
                                           _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
     "srcv_warp_workspace_bytes": (C.c_size_t, [C.POINTER(Shape)]),
     "srcv_warp_features_f32": (C.c_int32, [C.POINTER(Shape), _fp, C.POINTER(Cameras), _fp, C.c_int32,
                                            _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
     "srcv_mlp_workspace_bytes": (C.c_size_t, [C.POINTER(Shape), C.POINTER(MlpWeights)]),
+    "srcv_mlp_packed_bytes": (C.c_size_t, [C.POINTER(Shape), C.POINTER(MlpWeights)]),
+    "srcv_mlp_pack_weights": (C.c_int32, [C.POINTER(Shape), C.POINTER(MlpWeights), _fp, _fp]),
     "srcv_mlp_forward_f32": (C.c_int32, [C.POINTER(Shape), _fp, _fp, C.POINTER(Cameras),
                                          C.POINTER(Planes), C.POINTER(MlpWeights), _fp, _fp, _fp,
                                          _fp, C.c_size_t, _fp]),
     "srcv_mlp_backward_workspace_bytes": (C.c_size_t, [C.POINTER(Shape), C.POINTER(MlpWeights)]),
+    "srcv_mlp_backward_supported": (C.c_int32, [C.POINTER(Shape), C.c_int32, C.c_int32]),
     "srcv_mlp_backward_f32": (C.c_int32, [C.POINTER(Shape), _fp, _fp, C.POINTER(Cameras), C.POINTER(Planes),
                                           C.POINTER(MlpWeights), _fp, _fp, _fp, C.POINTER(MlpGrads), _fp,
                                           C.c_size_t, _fp]),
@@ -105,8 +109,8 @@ def load() -> C.CDLL:
             raise NativeLibraryError(f"{path} does not export {name}") from e
         fn.restype = res
         fn.argtypes = args
-    if lib.srcv_abi_version() != 1:
-        raise NativeLibraryError(f"ABI version mismatch: library {lib.srcv_abi_version()}, binding 1")
+    if lib.srcv_abi_version() != 2:
+        raise NativeLibraryError(f"ABI version mismatch: library {lib.srcv_abi_version()}, binding 2")
     _lib = lib
     return lib
 

@@ -25,6 +25,9 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
 ]
+# Preprocessor switches of the shipped build.  tests/emu compiles the same sources with the same
+# list, so the host emulation (parity, TSan, fuzzing) validates the binary that ships.
+NVCC_DEFINES: list[str] = []
 
 
 def nvcc_path() -> str:
@@ -49,7 +52,7 @@ def build(force: bool = False, verbose: bool = False, out: Path | None = None, e
         return OUT
     out = Path(out) if out else OUT
     out.parent.mkdir(parents=True, exist_ok=True)
-    cmd = [nvcc_path(), *NVCC_FLAGS, *(extra or []), *(["-Xptxas", "-v"] if verbose else []),
+    cmd = [nvcc_path(), *NVCC_FLAGS, *NVCC_DEFINES, *(extra or []), *(["-Xptxas", "-v"] if verbose else []),
            "-o", str(out), *map(str, SRC)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:

@@ -40,14 +40,35 @@ def _ptr(t: Tensor | None):
 def _f32c(t: Tensor, name: str, device) -> Tensor:
     if not torch.is_tensor(t):
         raise TypeError(f"{name} must be a tensor")
+    if t.dtype in (torch.float16, torch.bfloat16):
+        # autocast producers (the reference trains and validates at precision=16, train.py:132, and
+        # casts its sampling grid with type_as(src_feats), modules/cost_volume.py:208,597): the
+        # kernels compute in fp32, so half inputs are upcast — in the no-grad path exactly as in
+        # the autograd Functions below
+        t = t.float()
     if t.dtype != torch.float32:
-        raise ValueError(f"{name} must be float32 (got {t.dtype}); the fused path is fp32-only")
+        raise ValueError(f"{name} must be float32, float16 or bfloat16 (got {t.dtype})")
     if t.device != device:
         raise ValueError(f"{name} is on {t.device}, expected {device}")
     t = t.contiguous()
     if t.data_ptr() % 16 != 0:      # the kernels use 16-byte vector loads
         t = t.clone()
     return t
+
+
+def _check_backward_supported(kind: str, src_shape, hidden) -> None:
+    """Unsupported training shapes fail in forward(), not at backward() time."""
+    lib = _native.load()
+    B, K, Cc, H, W = src_shape
+    shape = _native.Shape(B, K, Cc, H, W, 1)
+    if kind == "dot":
+        if lib.srcv_dot_backward_supported(C.byref(shape)) == 0:
+            raise NotImplementedError(f"dot-product volume backward is built for C in {{8, 16, 32}}, got C={Cc}")
+    else:
+        if lib.srcv_mlp_backward_supported(C.byref(shape), int(hidden[0]), int(hidden[1])) == 0:
+            raise NotImplementedError(
+                "metadata-MLP volume backward: at most 208 input features and hidden widths <= 128 "
+                f"(K={K}, C={Cc}, hidden={tuple(hidden)})")
 
 
 class _DotVolumeFunction(torch.autograd.Function):
@@ -59,15 +80,23 @@ class _DotVolumeFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mgr, cur_feats, src_feats, src_extrinsics, src_Ks, cur_invK, min_depth, max_depth,
                 depth_planes_bdhw):
-        cur32, src32 = cur_feats.float(), src_feats.float()
+        dev = src_feats.device
+        # What is saved for the backward kernel is what the forward kernel read: dense, 16-byte
+        # aligned fp32 copies.  The caller's own tensors may be strided views — the reference
+        # passes cur_feats = matching_feats[:, 0] (experiment_modules/depth_model.py:242) — and the
+        # kernels index them as dense NCHW.
+        cur32, src32 = _f32c(cur_feats, "cur_feats", dev), _f32c(src_feats, "src_feats", dev)
+        E32, Ks32 = _f32c(src_extrinsics, "src_extrinsics", dev), _f32c(src_Ks, "src_Ks", dev)
+        invK32 = _f32c(cur_invK, "cur_invK", dev)
+        _check_backward_supported("dot", src32.shape, None)
         cost, lowest, planes_ret, _ = mgr._run_fused(
-            cur32, src32, src_extrinsics.float(), None, src_Ks.float(), cur_invK.float(), min_depth,
+            cur32, src32, E32, None, Ks32, invK32, min_depth,
             max_depth, depth_planes_bdhw, True, allow_grad=True)
         B, D, H, W = cost.shape
         st = planes_ret.stride()
         per_pixel = not ((st[2] == 0 or H == 1) and (st[3] == 0 or W == 1))
         planes = planes_ret[:, :D].contiguous() if per_pixel else planes_ret[:, :D, 0, 0].contiguous()
-        ctx.save_for_backward(cur32, src32, src_extrinsics.float(), src_Ks.float(), cur_invK.float(), planes)
+        ctx.save_for_backward(cur32, src32, E32, Ks32, invK32, planes)
         ctx.per_pixel = per_pixel
         ctx.in_dtypes = (cur_feats.dtype, src_feats.dtype)
         ctx.mark_non_differentiable(lowest, planes_ret)
@@ -81,8 +110,8 @@ class _DotVolumeFunction(torch.autograd.Function):
         B, K, Cc, H, W = src.shape
         D = grad_cost.shape[1]
         shape = _native.Shape(B, K, Cc, H, W, D)
-        cams = _native.Cameras(E.contiguous().data_ptr(), None, Ks.contiguous().data_ptr(),
-                               invK.contiguous().data_ptr())
+        # saved tensors are the dense aligned copies the forward made (see forward)
+        cams = _native.Cameras(E.data_ptr(), None, Ks.data_ptr(), invK.data_ptr())
         pl = _native.Planes()
         pl.mode = _native.PLANES_PER_PIXEL if ctx.per_pixel else _native.PLANES_PER_PLANE
         pl.planes = planes.data_ptr()
@@ -109,8 +138,11 @@ class _MlpVolumeFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mgr, return_mask, cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK,
                 min_depth, max_depth, depth_planes_bdhw, w1, b1, w2, b2, w3, b3):
-        cur32, src32 = cur_feats.float(), src_feats.float()
-        cams = [t.float() for t in (src_extrinsics, src_poses, src_Ks, cur_invK)]
+        dev = src_feats.device
+        cur32, src32 = _f32c(cur_feats, "cur_feats", dev), _f32c(src_feats, "src_feats", dev)
+        cams = [_f32c(t, n, dev) for t, n in ((src_extrinsics, "src_extrinsics"), (src_poses, "src_poses"),
+                                              (src_Ks, "src_Ks"), (cur_invK, "cur_invK"))]
+        _check_backward_supported("mlp", src32.shape, (w1.shape[0], w2.shape[0]))
         cost, lowest, planes_ret, mask = mgr._run_fused(
             cur32, src32, cams[0], cams[1], cams[2], cams[3], min_depth, max_depth, depth_planes_bdhw,
             return_mask, True, allow_grad=True)
@@ -134,14 +166,13 @@ class _MlpVolumeFunction(torch.autograd.Function):
         B, K, Cc, H, W = src.shape
         D = grad_cost.shape[1]
         shape = _native.Shape(B, K, Cc, H, W, D)
-        keep = [t.contiguous() for t in (E, P, Ks, invK)]
-        cams = _native.Cameras(*[t.data_ptr() for t in keep])
+        cams = _native.Cameras(E.data_ptr(), P.data_ptr(), Ks.data_ptr(), invK.data_ptr())
         pl = _native.Planes()
         pl.mode = _native.PLANES_PER_PIXEL if ctx.per_pixel else _native.PLANES_PER_PLANE
         pl.planes = planes.data_ptr()
         pl.min_depth = pl.max_depth = pl.ramp = pl.planes_out = None
         wc = [_f32c(t.detach(), "mlp parameter", dev) for t in wts]
-        w = _native.MlpWeights(*[t.data_ptr() for t in wc], wc[0].shape[0], wc[2].shape[0])
+        w = _native.MlpWeights(*[t.data_ptr() for t in wc], wc[0].shape[0], wc[2].shape[0], None)
         g = grad_cost.float().contiguous()
         with torch.cuda.device(dev):
             gcur, gsrc = torch.empty_like(cur), torch.empty_like(src)
@@ -271,8 +302,12 @@ class CostVolumeManager(nn.Module):
         if depth_planes_bdhw is None:
             mn = _f32c(min_depth.to(dev), "min_depth", dev).reshape(-1)
             mx = _f32c(max_depth.to(dev), "max_depth", dev).reshape(-1)
-            if mn.numel() != 1 or mx.numel() != 1:
-                raise ValueError("min_depth / max_depth must hold one value (shape (1,1,1,1))")
+            # one range for the batch ((1,1,1,1), depth_model.py:358-359) or one per frame
+            # ((B,1,1,1): generate_depth_planes broadcasts it, reference :124-127)
+            if mn.numel() != mx.numel() or mn.numel() not in (1, B):
+                raise ValueError("min_depth / max_depth must hold one value or one value per frame "
+                                 f"(got {mn.numel()} / {mx.numel()} for a batch of {B})")
+            pl.range_per_frame = int(mn.numel() == B and B > 1)
             ramp = _f32c(self.linear_ramp_1d11, "linear_ramp_1d11", dev).reshape(-1)
             planes_bd = torch.empty(B, D, device=dev, dtype=torch.float32)
             pl.mode = _native.PLANES_FROM_RANGE
@@ -396,8 +431,32 @@ class FeatureVolumeManager(CostVolumeManager):
             if l.bias is None:
                 raise NotImplementedError("MLP layers without bias are not supported")
             ts += [_f32c(l.weight.detach(), "mlp weight", dev), _f32c(l.bias.detach(), "mlp bias", dev)]
-        w = _native.MlpWeights(*[x.data_ptr() for x in ts], lin[0].out_features, lin[1].out_features)
+        w = _native.MlpWeights(*[x.data_ptr() for x in ts], lin[0].out_features, lin[1].out_features, None)
         return w, ts
+
+    def _attach_packed_image(self, dev, shape, w, ts):
+        """Points ``w.packed_image`` at the tensor-core kernel's fp16 weight image, re-packing it
+        (``srcv_mlp_pack_weights``) only when a parameter changed: the cache key is every
+        parameter's (storage address, version counter).  Returns what must stay alive."""
+        lib = _native.load()
+        nbytes = lib.srcv_mlp_packed_bytes(C.byref(shape), C.byref(w))
+        if nbytes == 0:
+            return None                                   # SIMT variant: nothing to pack
+        try:
+            key = (str(dev), tuple((t.data_ptr(), t._version) for t in ts))
+        except RuntimeError:                              # inference tensors carry no version counter
+            key = None
+        cache = self.__dict__.get("_srcv_packed")
+        if key is None or cache is None or cache[0] != key:
+            with torch.cuda.device(dev):
+                image = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+                _native.check(lib.srcv_mlp_pack_weights(
+                    C.byref(shape), C.byref(w), _ptr(image),
+                    C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+            cache = (key, image)
+            self.__dict__["_srcv_packed"] = cache         # plain attribute: not a buffer, not in state_dict
+        w.packed_image = cache[1].data_ptr()
+        return cache[1]
 
     def _run(self, cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK, min_depth,
              max_depth, depth_planes_bdhw, return_mask, want_lowest):
@@ -424,6 +483,7 @@ class FeatureVolumeManager(CostVolumeManager):
             max_depth, depth_planes_bdhw, need_poses=True, allow_grad=allow_grad)
         n_features = shape.C * (shape.K + 1) + 10 * shape.K + 4
         w, wkeep = self._mlp_weights(dev, n_features)
+        wkeep.append(self._attach_packed_image(dev, shape, w, wkeep))
         with torch.cuda.device(dev):
             cost = torch.empty(shape.B, shape.D, shape.H, shape.W, device=dev, dtype=torch.float32)
             lowest = torch.empty(shape.B, shape.H, shape.W, device=dev, dtype=torch.float32) \

@@ -181,6 +181,10 @@ size_t srcv_dot_backward_workspace_bytes(const srcv_shape* s) {
   return carve_workspace(*s, nullptr, false, 0).bytes;
 }
 
+int32_t srcv_dot_backward_supported(const srcv_shape* s) {
+  return (check_shape(s) == SRCV_OK && dot_backward_supported(*s)) ? 1 : 0;
+}
+
 int32_t srcv_dot_backward_f32(const srcv_shape* s, const float* cur, const float* src,
                               const srcv_cameras* cams, const srcv_planes* pl, const float* grad_cost,
                               float* grad_cur, float* grad_src, void* workspace,
@@ -261,6 +265,24 @@ size_t srcv_mlp_workspace_bytes(const srcv_shape* s, const srcv_mlp_weights* w) 
   return carve_workspace(*s, nullptr, mlp_tc_supported(*s, *w), mlp_extra_bytes(*s, *w)).bytes;
 }
 
+size_t srcv_mlp_packed_bytes(const srcv_shape* s, const srcv_mlp_weights* w) {
+  if (check_shape(s) != SRCV_OK || !w) return 0;
+  return mlp_tc_supported(*s, *w) ? mlp_tc_image_bytes() : 0;
+}
+
+int32_t srcv_mlp_pack_weights(const srcv_shape* s, const srcv_mlp_weights* w, void* image, void* stream_) {
+  if (int32_t e = check_shape(s)) return e;
+  if (int32_t e = check_weights(s, w)) return e;
+  if (!mlp_tc_supported(*s, *w))
+    return fail(SRCV_ERR_UNSUPPORTED, "only the tensor-core variant (K == 7, C == 16, hidden 128/128) has a packed image");
+  if (!image) return fail(SRCV_ERR_NULL, "image is NULL");
+  if ((reinterpret_cast<uintptr_t>(image) & 255u) != 0)
+    return fail(SRCV_ERR_WORKSPACE, "image must be 256-byte aligned");
+  cudaError_t err = launch_mlp_tc_pack(*w, image, static_cast<cudaStream_t>(stream_));
+  if (err != cudaSuccess) return cuda_fail(err, "pack");
+  return SRCV_OK;
+}
+
 int32_t srcv_mlp_forward_f32(const srcv_shape* s, const float* cur, const float* src,
                              const srcv_cameras* cams, const srcv_planes* pl,
                              const srcv_mlp_weights* w, float* cost, float* lowest,
@@ -302,6 +324,14 @@ size_t srcv_mlp_backward_workspace_bytes(const srcv_shape* s, const srcv_mlp_wei
   if (check_shape(s) != SRCV_OK || !w) return 0;
   if (!mlp_backward_supported(*s, *w)) return 0;
   return carve_workspace(*s, nullptr, false, mlp_backward_extra_bytes(*s, *w)).bytes;
+}
+
+int32_t srcv_mlp_backward_supported(const srcv_shape* s, int32_t hidden1, int32_t hidden2) {
+  if (check_shape(s) != SRCV_OK) return 0;
+  srcv_mlp_weights w{};
+  w.hidden1 = hidden1;
+  w.hidden2 = hidden2;
+  return mlp_backward_supported(*s, w) ? 1 : 0;
 }
 
 int32_t srcv_mlp_backward_f32(const srcv_shape* s, const float* cur, const float* src,

@@ -46,7 +46,7 @@ constexpr float kEpsCos = 1e-5f;    // modules/cost_volume.py:687
 constexpr float kLeaky = 0.01f;     // nn.LeakyReLU default slope
 
 // Per (frame b, view k) constants, written by prep_kernel.  32 floats = 128 B.
-struct ViewParams {
+struct __align__(16) ViewParams {
   float a0[3];     // centred homography applied to the image centre
   float hx[3];     // d a'/d dx  (column 0 of the centred Hm)
   float hy[3];     // d a'/d dy  (column 1)
@@ -55,13 +55,15 @@ struct ViewParams {
   float comb;      // pose_distance: sqrt(t_meas^2 + r_meas^2)
   float rmeas;     // sqrt(2 (1 - min(3, tr R)/3))
   float tmeas;     // |src_poses[:3,3]|
-  float pad[14];
+  uint32_t rt_hi;  // (rmeas, tmeas) as the fp16 (hi, lo) operand words of the tcgen05 kernel
+  uint32_t rt_lo;  //   (csrc/srcv_tc.cuh split_pack), so the sweep does not re-split constants
+  float pad[12];
 };
 static_assert(sizeof(ViewParams) == 128, "ViewParams must be 128 bytes");
 constexpr int kViewFloats = 12;  // a0, hx, hy, t: what the sweep kernels stage in smem
 
 // Per frame constants: invK[:3,:3] (row-major) for the ray r = invK3 p.
-struct FrameParams {
+struct __align__(16) FrameParams {
   float invK[9];
   float pad[7];
 };
@@ -150,7 +152,7 @@ __device__ __forceinline__ float inv_norm(float s, float eps) {
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(s));
 #endif
   y = y * fmaf(-0.5f * s, y * y, 1.5f);
-  return (s > eps * eps) ? y : __frcp_rn(eps);
+  return (s > eps * eps) ? y : (1.0f / eps);   // eps is a literal at every call site: folds to a constant
 }
 
 // argmax update with torch.argmax semantics: first index wins ties, NaN is max.

@@ -85,6 +85,8 @@ cudaError_t launch_mlp_backward(const srcv_shape& s, const float* cur, const flo
 // tensor-core variant (tcgen05): K = 7, C = 16, 202 -> 128 -> 128 -> 1
 bool mlp_tc_supported(const srcv_shape& s, const srcv_mlp_weights& w);
 size_t mlp_tc_extra_bytes();
+size_t mlp_tc_image_bytes();
+cudaError_t launch_mlp_tc_pack(const srcv_mlp_weights& w, void* image, cudaStream_t stream);
 cudaError_t launch_mlp_tc(const srcv_shape& s, const float* cur, const Workspace& ws,
                           const float* planes, bool per_pixel, const srcv_mlp_weights& w, float* cost,
                           float* lowest, uint8_t* mask, cudaStream_t stream);

@@ -13,24 +13,32 @@
 //      (tcgen05.st) — the (B,F,H,W) / (B*D,H,W,F) tensors the reference materialises exist
 //      only as 208 TMEM columns per row;
 //   2. layer 1 = 13 x 3 tcgen05.mma (A from TMEM, weights from shared memory, fp32
-//      accumulator in TMEM):  A_hi W_hi + A_hi W_lo + A_lo W_hi;
-//   3. the workers read the accumulator (each its 32 columns), add bias, LeakyReLU, split to
-//      fp16 (hi, lo) again and write the layer-2 A operand back to TMEM;
-//   4. layer 2 = 8 x 3 tcgen05.mma into the same accumulator columns;
+//      accumulator in TMEM):  A_hi W_hi + A_hi W_lo + A_lo W_hi.  The bias rides in the MMA
+//      (a constant-one K position against a 16 b1 weight row);
+//   3. the workers read the accumulator (each its 32 columns), apply LeakyReLU, split to
+//      fp16 (hi, lo) and write the layer-2 A operand back IN PLACE — a thread's 32 fp32
+//      accumulator columns become its 16 hi + 16 lo operand columns, so no other thread's
+//      columns are touched and no cross-thread ordering is needed;
+//   4. layer 2 = 8 x 3 tcgen05.mma into a SECOND accumulator region;
 //   5. the workers apply bias + LeakyReLU and the 128 -> 1 layer as partial dots, reduced in
 //      a fixed order through shared memory, and store the cost.
-// Stages are chained by mbarriers (tcgen05.commit for MMA completion).  A worker builds the
-// first K block of tile t+1 while tile t's layer-1 MMAs run and the second one while its
-// layer-2 MMAs run, so the tensor pipe and the SIMT pipes overlap.
+// Stages are chained by mbarriers (tcgen05.commit for MMA completion).  Because layer 2
+// accumulates into its own TMEM columns, the layer-1 MMAs of tile t+1 run while the workers
+// are still in step 5 of tile t; a worker builds the first K block of tile t+1 while tile
+// t's layer-1 MMAs run and the second one while its layer-2 MMAs run.  The tensor pipe only
+// idles during step 3.
 // Weights (both layers, hi and lo, 168 KB) stay resident in shared memory for the
 // CTA's lifetime, laid out as K-major no-swizzle core matrices by the pack kernel.
 //
 // The K order of layer 1 is OURS (the pack kernel permutes W1's columns to match):
 //   per view k (26 channels): 16 warped | mask | z' | dot | ray angle | n_src (3) | comb | r | t
-//   tail (20 + 6 pad):        16 reference features | plane depth | n_cur (3) | zeros
-// i.e. every worker thread writes 2 x 26 = 52 consecutive K positions; the first of its
-// two blocks is computed before it waits for the A columns to be free, so producing tile
-// t+1 overlaps the layer-1 MMAs of tile t.
+//   tail (21 + 5 pad):        16 reference features | plane depth | n_cur (3) | ONE (bias) | zeros
+// i.e. every worker thread writes 2 x 26 = 52 consecutive K positions.
+//
+// Scaling: W1 and W2 are stored x16 (exact) so the lo halves of typical |w| ~ 0.05 weights
+// stay out of the fp16 subnormals.  Layer 1 therefore yields 16 (W1 x + b1); LeakyReLU
+// commutes with the positive scale, so the layer-2 operand is 16 a and its accumulator is
+// 256 (W2 a): the single 1/256 is folded into the layer-2 bias FMA.
 #include "srcv_kernels.h"
 #include "srcv_tc.cuh"
 
@@ -48,39 +56,40 @@ constexpr int kRows = 128;               // rows (TMEM lanes) per tile
 constexpr int kTileW = 16, kTileH = 2, kTileD = 4;
 constexpr int kN = 128;                  // layer widths
 constexpr int kBlk = kC + 10;            // channels per view block (26)
-constexpr int kK1 = 208;                 // 7*26 + 20 + 6 pad  (13 k-steps of 16)
+constexpr int kK1 = 208;                 // 7*26 + 21 + 5 pad  (13 k-steps of 16)
 constexpr int kK2 = 128;
 constexpr int kF = kC * (kViews + 1) + 10 * kViews + 4;  // 202
+constexpr int kBiasPos = kViews * kBlk + kC + 4;         // K position of the constant one
 
 // TMEM columns (32-bit): two K elements per column
-constexpr uint32_t kColA1Hi = 0, kColA1Lo = kK1 / 2, kColD = kK1, kColA2Hi = kK1 + kN,
-                   kColA2Lo = kK1 + kN + kK2 / 2, kTmemCols = 512;
-static_assert(kColA2Lo + kK2 / 2 <= kTmemCols, "TMEM budget");
+//   A1 hi | A1 lo | DA (layer-1 accumulator, then the layer-2 operand in place) | D2
+constexpr uint32_t kColA1Hi = 0, kColA1Lo = kK1 / 2, kColDA = kK1, kColD2 = kK1 + kN, kTmemCols = 512;
+static_assert(kColD2 + kN <= kTmemCols, "TMEM budget");
 
-// Weights are stored x16 (exact) so that the lo halves of typical |w| ~ 0.05 weights stay
-// out of the fp16 subnormal range; the epilogues fold the 1/16 into their bias FMA.
-constexpr float kWScale = 16.0f, kWUnscale = 1.0f / 16.0f;
+constexpr float kWScale = 16.0f;
+constexpr float kUnscale2 = 1.0f / (kWScale * kWScale);
 
 // 16 "row worker" warps: four threads per row (quarter q = warp / 4).  Every worker is
 // producer AND epilogue of its rows — it builds K blocks {2q, 2q+1} of the A operand and
-// post-processes accumulator columns [32q, 32q+32) — so the epilogues, which sit on the
-// per-tile critical path MMA1 -> epi1 -> MMA2 -> epi2, get all 16 warps' issue slots
-// instead of competing with separate producer warps.  Warp 16 issues the MMAs; warps
-// 17-19 only pad the block to a 4-warp allocation unit (20 warps x 96 registers).
+// post-processes accumulator columns [32q, 32q+32).  Warp 16 issues the MMAs; warps 17-19
+// complete its warpgroup (setmaxnreg works on aligned groups of four warps): the kernel is
+// launched at 96 registers per thread, the MMA group shrinks to 24 and the 16 worker warps
+// grow to 120 — room for all 16 vector loads of a bilinear footprint in flight.
 constexpr int kWorkWarps = 16, kMmaWarp = 16;
 constexpr int kThreads = 20 * 32;
 constexpr int kWorkers = kWorkWarps * 32;
+constexpr int kRegsWorker = 120, kRegsMma = 24;
 
 // shared memory image (bytes)
 constexpr uint32_t kW1Bytes = kN * kK1 * 2, kW2Bytes = kN * kK2 * 2;   // one of (hi, lo)
 constexpr uint32_t kOffW1Hi = 0, kOffW1Lo = kW1Bytes, kOffW2Hi = 2 * kW1Bytes,
                    kOffW2Lo = 2 * kW1Bytes + kW2Bytes, kOffVec = 2 * kW1Bytes + 2 * kW2Bytes;
-constexpr uint32_t kVecFloats = 3 * kN + 4;   // b1 | b2 | w3 | b3
+constexpr uint32_t kVecFloats = 3 * kN + 4;   // b2 | 0.505 w3 | 0.495 w3 | b3
 constexpr uint32_t kOffBar = kOffVec + kVecFloats * 4;
 constexpr uint32_t kOffFlag = kOffBar + 8 * 8;            // 8 mbarrier slots
 constexpr uint32_t kOffPart = kOffFlag + 2 * 4 * kRows;   // mask bits [parity][quarter][row]
 constexpr uint32_t kSmemBytes = kOffPart + 2 * 4 * kRows * 4;  // layer-3 partial dots [parity][quarter][row]
-// image = [W1hi | W1lo | W2hi | W2lo | b1 b2 w3 b3] exactly as it sits in shared memory
+// image = [W1hi | W1lo | W2hi | W2lo | vec] exactly as it sits in shared memory
 constexpr uint32_t kImageBytes = kOffBar;
 
 // K-major no-swizzle core-matrix offset (in halves) of element (n, k) of an N x Kp operand
@@ -88,7 +97,8 @@ __host__ __device__ inline uint32_t core_offset(int n, int k, int N) {
   return (uint32_t)(k >> 3) * (uint32_t)(N * 8) + (uint32_t)(n >> 3) * 64u + (uint32_t)(n & 7) * 8u + (uint32_t)(k & 7);
 }
 
-// reference channel index (modules/cost_volume.py:698-723 order) of OUR layer-1 K position
+// reference channel index (modules/cost_volume.py:698-723 order) of OUR layer-1 K position;
+// -2 = the bias position (constant one in A), -1 = padding
 __host__ __device__ inline int ref_channel(int kk) {
   if (kk < kViews * kBlk) {
     const int k = kk / kBlk, j = kk - k * kBlk;
@@ -109,6 +119,7 @@ __host__ __device__ inline int ref_channel(int kk) {
   if (j < kC) return kViews * kC + j;                    // reference-frame features
   if (j == kC) return kC * (kViews + 1) + 2 * kViews;    // plane depth
   if (j < kC + 4) return kC * (kViews + 1) + 4 * kViews + 1 + (j - kC - 1);  // n_cur
+  if (kk == kBiasPos) return -2;                         // bias
   return -1;                                             // pad
 }
 
@@ -126,7 +137,7 @@ tc_pack_kernel(srcv_mlp_weights w, uint8_t* __restrict__ image) {
     if (i < n1) {
       const int n = i / kK1, kk = i - n * kK1;
       const int f = ref_channel(kk);
-      const float v = kWScale * (f >= 0 ? w.w1[(size_t)n * kF + f] : 0.f);
+      const float v = kWScale * (f >= 0 ? w.w1[(size_t)n * kF + f] : (f == -2 ? w.b1[n] : 0.f));
       const __half h = __float2half_rn(v);
       w1hi[core_offset(n, kk, kN)] = h;
       w1lo[core_offset(n, kk, kN)] = __float2half_rn(v - __half2float(h));
@@ -137,22 +148,18 @@ tc_pack_kernel(srcv_mlp_weights w, uint8_t* __restrict__ image) {
       w2hi[core_offset(n, kk, kN)] = h;
       w2lo[core_offset(n, kk, kN)] = __float2half_rn(v - __half2float(h));
     } else {
+      // LeakyReLU(h) w3 = (0.505 w3) h + (0.495 w3) |h|  (slope 0.01): two FMAs per column
       const int q = i - n1 - n2;
       float v = 0.f;
-      if (q < kN) v = w.b1[q];
-      else if (q < 2 * kN) v = w.b2[q - kN];
-      else if (q < 3 * kN) v = w.w3[q - 2 * kN];
+      if (q < kN) v = w.b2[q];
+      else if (q < 2 * kN) v = (0.5f * (1.0f + kLeaky)) * w.w3[q - kN];
+      else if (q < 3 * kN) v = (0.5f * (1.0f - kLeaky)) * w.w3[q - 2 * kN];
       else if (q == 3 * kN) v = w.b3[0];
       vec[q] = v;
     }
   }
 }
 
-// 26 values of one K block -> 13 packed (hi, lo) column pairs
-__device__ __forceinline__ void split_block(const float (&v)[kBlk], uint32_t (&hi)[13], uint32_t (&lo)[13]) {
-#pragma unroll
-  for (int i = 0; i < 13; ++i) split_pack(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
-}
 // 13 packed columns of one K block -> TMEM (hi and lo regions)
 __device__ __forceinline__ void store_block(uint32_t tbase_lane, uint32_t col, const uint32_t (&hi)[13],
                                             const uint32_t (&lo)[13]) {
@@ -164,78 +171,93 @@ __device__ __forceinline__ void store_block(uint32_t tbase_lane, uint32_t col, c
   st_x1(tbase_lane + kColA1Lo + col + 12, lo[12]);
 }
 
-// Per-row quantities shared by the view blocks of one tile.
+// What a worker thread keeps about the tile it builds the A operand for.
 struct RowCtx {
   float dval, dxc, dyc;      // plane depth, centred pixel
   float X, Y, Z;             // back-projected point
   float cxn, cyn, czn;       // n_cur / max(|n_cur|, eps_cos)  (cosine_similarity operand)
+  float cx, cy, cz;          // n_cur
   float4 cur4[4];            // reference-frame features of the pixel
+  int b;                     // frame
+  long long out;             // offset of the row's cost element, < 0 for rows outside the volume
+  bool last_plane;           // the row's plane is D - 1 (the overall mask is taken there)
 };
 
-// One source view of one row: project, gather, metadata (channel order of the K block).
-// HWC != 0: compile-time map size, every gather address is base + immediate.
+// The depth-invariant part of one (frame, view): five 16-byte loads (ViewParams is 128-byte
+// aligned; the struct order a0 hx hy t | centre comb | rmeas tmeas rt_hi rt_lo is what they read).
+struct ViewRegs {
+  float a0[3], hx[3], hy[3], t[3], centre[3], comb;
+  uint32_t rt_hi, rt_lo;     // (rmeas, tmeas) already split and packed by the prep kernel
+};
+__device__ __forceinline__ void load_view(const ViewParams* __restrict__ vp, ViewRegs& v) {
+  const float4* p = reinterpret_cast<const float4*>(vp);
+  const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3), e = __ldg(p + 4);
+  v.a0[0] = a.x; v.a0[1] = a.y; v.a0[2] = a.z; v.hx[0] = a.w;
+  v.hx[1] = b.x; v.hx[2] = b.y; v.hy[0] = b.z; v.hy[1] = b.w;
+  v.hy[2] = c.x; v.t[0] = c.y; v.t[1] = c.z; v.t[2] = c.w;
+  v.centre[0] = d.x; v.centre[1] = d.y; v.centre[2] = d.z; v.comb = d.w;
+  v.rt_hi = __float_as_uint(e.z); v.rt_lo = __float_as_uint(e.w);
+}
+
+// One source view of one row: project, gather, metadata -> the 13 (hi, lo) column pairs of
+// the K block.  HWC != 0: compile-time map size, every gather address is base + immediate.
+// WANT_BITS (warp-uniform): also return the depth-valid / in-bounds bits of the overall mask.
 template <int TW, int HWC>
-__device__ __forceinline__ unsigned view_block(const RowCtx& rc, const ViewParams& vp,
+__device__ __forceinline__ unsigned view_block(const RowCtx& rc, const ViewParams* __restrict__ vpp,
                                                const float4* __restrict__ view4, int Wrt, int H, int HWrt,
-                                               const Centre& ctr, float (&v)[kBlk]) {
+                                               const Centre& ctr, bool want_bits, uint32_t (&hi)[13],
+                                               uint32_t (&lo)[13]) {
   const int W = TW ? TW : Wrt, HW = HWC ? HWC : HWrt;
-  float ax, ay, az, px, py, zp;
-  homography_point(vp.a0, rc.dxc, rc.dyc, ax, ay, az);
-  project_point(rc.dval, ax, ay, az, vp.t[0], vp.t[1], vp.t[2], px, py, zp);
-  Taps tp;
-  bilinear_taps(px, py, W, H, ctr, tp);
-  const float gx = 1.0f - tp.fx, gy = 1.0f - tp.fy;
-  const float wgt[4] = {gx * gy, tp.fx * gy, gx * tp.fy, tp.fx * tp.fy};
-  const int off[4] = {0, 1, W, W + 1};
-  const float4* q = view4 + (tp.y0 * W + tp.x0);
+  ViewRegs vr;
+  load_view(vpp, vr);
+  const float ax = fmaf(vr.hx[0], rc.dxc, fmaf(vr.hy[0], rc.dyc, vr.a0[0]));
+  const float ay = fmaf(vr.hx[1], rc.dxc, fmaf(vr.hy[1], rc.dyc, vr.a0[1]));
+  const float az = fmaf(vr.hx[2], rc.dxc, fmaf(vr.hy[2], rc.dyc, vr.a0[2]));
+  float px, py, zp;
+  project_point(rc.dval, ax, ay, az, vr.t[0], vr.t[1], vr.t[2], px, py, zp);
+  // bilinear footprint.  Warp-uniform fast path: every lane's 2 x 2 footprint lies inside the
+  // map (float compares: NaN / inf coordinates fail them and take the general path).
+  const float x0f = floorf(px), y0f = floorf(py);
+  const float fx = px - x0f, fy = py - y0f;
+  const bool inside = x0f >= -(float)ctr.nx && x0f <= (float)(W - 2 - ctr.nx) &&
+                      y0f >= -(float)ctr.ny && y0f <= (float)(H - 2 - ctr.ny);
+  const bool interior = __all_sync(0xffffffffu, inside);
+  const float gx = 1.0f - fx, gy = 1.0f - fy;
+  float w00 = gx * gy, w01 = fx * gy, w10 = gx * fy, w11 = fx * fy;
+  int o00, o01, o10, o11;
+  if (interior) {
+    o00 = ((int)y0f + ctr.ny) * W + ((int)x0f + ctr.nx);
+    o01 = o00 + 1; o10 = o00 + W; o11 = o00 + W + 1;
+  } else {
+    // border patches, branch-free: every tap is loaded from an in-range (clamped) texel and
+    // padding taps get a zero weight (zeros padding of grid_sample).
+    Taps tp;
+    bilinear_taps(px, py, W, H, ctr, tp);
+    const int cxa = min(max(tp.x0, 0), W - 1), cxb = min(max(tp.x0 + 1, 0), W - 1);
+    const int cya = min(max(tp.y0, 0), H - 1) * W, cyb = min(max(tp.y0 + 1, 0), H - 1) * W;
+    o00 = cya + cxa; o01 = cya + cxb; o10 = cyb + cxa; o11 = cyb + cxb;
+    w00 = (tp.valid & 1u) ? w00 : 0.f; w01 = (tp.valid & 2u) ? w01 : 0.f;
+    w10 = (tp.valid & 4u) ? w10 : 0.f; w11 = (tp.valid & 8u) ? w11 : 0.f;
+  }
   // features are sampled even for points behind the camera (only the dot is masked,
-  // reference modules/cost_volume.py:590-623); padding taps contribute zeros
-  // two taps (8 vector loads) in flight at a time keeps the worker inside its register budget
-  const bool interior = __all_sync(0xffffffffu, tp.valid == 15u);
-#ifdef SRCV_TC_CLAMPED_TAPS
-  const int cxa = min(max(tp.x0, 0), W - 1), cxb = min(max(tp.x0 + 1, 0), W - 1);
-  const int cya = min(max(tp.y0, 0), H - 1) * W, cyb = min(max(tp.y0 + 1, 0), H - 1) * W;
-  const int coff[4] = {cya + cxa, cya + cxb, cyb + cxa, cyb + cxb};
-#endif
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    float4 f[2][4];
-#pragma unroll
-    for (int tt = 0; tt < 2; ++tt) {
-      const int tap = 2 * half + tt;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (interior) f[tt][j] = __ldg(q + off[tap] + (size_t)j * HW);
-#ifdef SRCV_TC_CLAMPED_TAPS
-        else {
-          // Round-2 experiment (off by default): branch-free borders.  Every tap is loaded from an
-          // in-range (clamped) texel and padding taps are zeroed by selects on the VALUES (not on
-          // the weights: a non-finite texel must not leak through 0 * inf) — instead of a
-          // BSSY / BRA / CS2R region around every conditional load.
-          const float4 tv = __ldg(view4 + coff[tap] + (size_t)j * HW);
-          const bool on = ((tp.valid >> tap) & 1u) != 0u;
-          f[tt][j] = make_float4(on ? tv.x : 0.f, on ? tv.y : 0.f, on ? tv.z : 0.f, on ? tv.w : 0.f);
-        }
-#else
-        else f[tt][j] = ((tp.valid >> tap) & 1u) ? __ldg(q + off[tap] + (size_t)j * HW)
-                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-#endif
-      }
-    }
-    const float wa = wgt[2 * half], wb = wgt[2 * half + 1];
+  // reference modules/cost_volume.py:590-623)
+  float v[kC];
+  {
+    const float4 *q0 = view4 + o00, *q1 = view4 + o01, *q2 = view4 + o10, *q3 = view4 + o11;
+    float4 f[4][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      if (half == 0) {
-        v[4 * j + 0] = fmaf(wa, f[0][j].x, wb * f[1][j].x);
-        v[4 * j + 1] = fmaf(wa, f[0][j].y, wb * f[1][j].y);
-        v[4 * j + 2] = fmaf(wa, f[0][j].z, wb * f[1][j].z);
-        v[4 * j + 3] = fmaf(wa, f[0][j].w, wb * f[1][j].w);
-      } else {
-        v[4 * j + 0] = fmaf(wa, f[0][j].x, fmaf(wb, f[1][j].x, v[4 * j + 0]));
-        v[4 * j + 1] = fmaf(wa, f[0][j].y, fmaf(wb, f[1][j].y, v[4 * j + 1]));
-        v[4 * j + 2] = fmaf(wa, f[0][j].z, fmaf(wb, f[1][j].z, v[4 * j + 2]));
-        v[4 * j + 3] = fmaf(wa, f[0][j].w, fmaf(wb, f[1][j].w, v[4 * j + 3]));
-      }
+      f[0][j] = __ldg(q0 + (size_t)j * HW);
+      f[1][j] = __ldg(q1 + (size_t)j * HW);
+      f[2][j] = __ldg(q2 + (size_t)j * HW);
+      f[3][j] = __ldg(q3 + (size_t)j * HW);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[4 * j + 0] = fmaf(w11, f[3][j].x, fmaf(w10, f[2][j].x, fmaf(w01, f[1][j].x, w00 * f[0][j].x)));
+      v[4 * j + 1] = fmaf(w11, f[3][j].y, fmaf(w10, f[2][j].y, fmaf(w01, f[1][j].y, w00 * f[0][j].y)));
+      v[4 * j + 2] = fmaf(w11, f[3][j].z, fmaf(w10, f[2][j].z, fmaf(w01, f[1][j].z, w00 * f[0][j].z)));
+      v[4 * j + 3] = fmaf(w11, f[3][j].w, fmaf(w10, f[2][j].w, fmaf(w01, f[1][j].w, w00 * f[0][j].w)));
     }
   }
   float dot = 0.f;
@@ -245,132 +267,114 @@ __device__ __forceinline__ unsigned view_block(const RowCtx& rc, const ViewParam
           fmaf(v[4 * j + 2], rc.cur4[j].z, fmaf(v[4 * j + 3], rc.cur4[j].w, dot))));
   const float mk = zp > 0.0f ? 1.0f : 0.0f;
   // n_src = (X - centre_k)/max(|.|, 1e-12) ; ray angle = cosine_similarity(n_cur, n_src, eps 1e-5)
-  const float sx0 = rc.X - vp.centre[0], sy0 = rc.Y - vp.centre[1], sz0 = rc.Z - vp.centre[2];
+  const float sx0 = rc.X - vr.centre[0], sy0 = rc.Y - vr.centre[1], sz0 = rc.Z - vr.centre[2];
   const float is = inv_norm(fmaf(sx0, sx0, fmaf(sy0, sy0, sz0 * sz0)), kEpsNorm);
   const float sx = sx0 * is, sy = sy0 * is, sz = sz0 * is;
   const float i2 = inv_norm(fmaf(sx, sx, fmaf(sy, sy, sz * sz)), kEpsCos);
-  v[kC + 0] = mk;
-  v[kC + 1] = zp;
-  v[kC + 2] = dot * mk;
-  v[kC + 3] = fmaf(rc.cxn, sx * i2, fmaf(rc.cyn, sy * i2, rc.czn * (sz * i2)));
-  v[kC + 4] = sx; v[kC + 5] = sy; v[kC + 6] = sz;
-  v[kC + 7] = vp.comb; v[kC + 8] = vp.rmeas; v[kC + 9] = vp.tmeas;
+  const float ang = fmaf(rc.cxn, sx * i2, fmaf(rc.cyn, sy * i2, rc.czn * (sz * i2)));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split_pack(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+  split_pack(mk, zp, hi[8], lo[8]);
+  split_pack(dot * mk, ang, hi[9], lo[9]);
+  split_pack(sx, sy, hi[10], lo[10]);
+  split_pack(sz, vr.comb, hi[11], lo[11]);
+  hi[12] = vr.rt_hi; lo[12] = vr.rt_lo;
   unsigned bits = 0;
-  if (zp > 0.0f) bits |= 1u;
-  if (in_mask_bounds(px, py, W, H, ctr)) bits |= 2u;
+  if (want_bits) {
+    if (zp > 0.0f) bits |= 1u;
+    if (in_mask_bounds(px, py, W, H, ctr)) bits |= 2u;
+  }
   return bits;
 }
 
-// issue D (+)= A_hi W_hi + A_hi W_lo + A_lo W_hi over KSTEPS K steps of 16
-template <int KSTEPS>
-__device__ __forceinline__ void issue_layer(uint32_t tmem_base, uint32_t col_hi, uint32_t col_lo,
+// The view-independent tail block: reference features | plane depth | n_cur | one | zeros
+__device__ __forceinline__ void tail_block(const RowCtx& rc, uint32_t (&hi)[13], uint32_t (&lo)[13]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    split_pack(rc.cur4[j].x, rc.cur4[j].y, hi[2 * j], lo[2 * j]);
+    split_pack(rc.cur4[j].z, rc.cur4[j].w, hi[2 * j + 1], lo[2 * j + 1]);
+  }
+  split_pack(rc.dval, rc.cx, hi[8], lo[8]);
+  split_pack(rc.cy, rc.cz, hi[9], lo[9]);
+  hi[10] = 0x00003C00u; lo[10] = 0u;      // (1.0, 0): the bias position
+  hi[11] = 0u; lo[11] = 0u;
+  hi[12] = 0u; lo[12] = 0u;
+}
+
+// issue D (+)= A_hi W_hi + A_hi W_lo + A_lo W_hi over KSTEPS K steps of 16.
+// LAYER2: the operand sits where the layer-1 accumulator was — k-step ks reads the hi columns
+// 32 (ks / 2) + 8 (ks % 2) and the lo columns 16 further (see the layer-1 epilogue).
+template <int KSTEPS, bool LAYER2>
+__device__ __forceinline__ void issue_layer(uint32_t d, uint32_t a_base, uint32_t a_lo_off,
                                             uint32_t smem_hi, uint32_t smem_lo) {
   constexpr uint32_t idesc = idesc_f16_f32(kRows, kN);
   constexpr uint32_t kLbo = kN * 16, kSbo = 128, kStepBytes = 2 * kLbo;  // two 8-wide K chunks per MMA
   // only the 14-bit start-address field changes from step to step
-  const uint64_t bhi0 = smem_desc(smem_hi, kLbo, kSbo), blo0 = smem_desc(smem_lo, kLbo, kSbo);
-  const uint32_t d = tmem_base + kColD;
-  uint64_t bhi = bhi0, blo = blo0;
-  uint32_t ahi = tmem_base + col_hi, alo = tmem_base + col_lo;
+  uint64_t bhi = smem_desc(smem_hi, kLbo, kSbo), blo = smem_desc(smem_lo, kLbo, kSbo);
 #pragma unroll 1
   for (int ks = 0; ks < KSTEPS; ++ks) {
+    const uint32_t ahi = LAYER2 ? a_base + 32u * (uint32_t)(ks >> 1) + 8u * (uint32_t)(ks & 1)
+                                : a_base + 8u * (uint32_t)ks;
+    const uint32_t alo = ahi + a_lo_off;
     mma_ts(d, ahi, bhi, idesc, ks > 0 ? 1u : 0u);
     mma_ts(d, ahi, blo, idesc, 1u);
     mma_ts(d, alo, bhi, idesc, 1u);
     bhi += kStepBytes >> 4; blo += kStepBytes >> 4;
-    ahi += 8; alo += 8;
   }
 }
 
-struct TileCoord { int b, d0, x0, y0; };
-
-// tile id runs plane-chunk fastest, then pixel patch, then frame
-__device__ __forceinline__ TileCoord tile_coord(long long id, int D, int tiles_x, int tiles_xy) {
-  TileCoord t;
-  const int nd = (D + kTileD - 1) / kTileD;
-#ifdef SRCV_TC_TILE32
-  // Round-2 experiment (off by default): tile ids fit 32 bits for every supported shape (the
-  // launcher refuses >= 2^31 tiles), and the 64-bit div/mod pairs cost ~120 instructions per
-  // thread and tile (two make_tile_row per tile) — 7 % of the worker's instruction budget.
-  const unsigned uid = (unsigned)id, und = (unsigned)nd, uxy = (unsigned)tiles_xy;
-  t.d0 = (int)(uid % und) * kTileD;
-  const unsigned r = uid / und;
-  const int txy = (int)(r % uxy);
-  t.b = (int)(r / uxy);
-#else
-  t.d0 = (int)(id % nd) * kTileD;
-  const long long r = id / nd;
-  const int txy = (int)(r % tiles_xy);
-  t.b = (int)(r / tiles_xy);
-#endif
-  t.x0 = (txy % tiles_x) * kTileW;
-  t.y0 = (txy / tiles_x) * kTileH;
-  return t;
-}
-
-// Row context of one tile for one worker thread (what the K blocks and the final store need).
-struct TileRow {
-  RowCtx rc;
-  float cx, cy, cz;   // n_cur
-  int b, d, p;        // frame, plane, pixel index (clamped into the map)
-  bool active;        // row maps to a real pixel (partial tiles at the right/bottom border)
-};
-
+// tile id runs plane-chunk fastest, then pixel patch, then frame (32-bit: the launcher
+// refuses >= 2^31 tiles); row -> (plane-in-chunk = row / 32, pixel of the 16 x 2 patch = row % 32)
 template <bool PER_PIXEL>
-__device__ __forceinline__ void make_tile_row(long long id, int row, int W, int H, int HW, int D,
-                                              int tiles_x, int tiles_xy, const Centre& ctr,
-                                              const FrameParams* __restrict__ frames,
-                                              const float* __restrict__ planes, TileRow& tr) {
-  const TileCoord t = tile_coord(id, D, tiles_x, tiles_xy);
-  // row -> (plane-in-chunk = row / 32, pixel of the 16 x 2 patch = row % 32)
+__device__ __forceinline__ void make_row(unsigned id, int row, int W, int H, int HW, int D, unsigned nd,
+                                         unsigned tiles_x, unsigned tiles_xy, const Centre& ctr,
+                                         const float4* __restrict__ cur4g,
+                                         const FrameParams* __restrict__ frames,
+                                         const float* __restrict__ planes, RowCtx& rc) {
+  const int d0 = (int)(id % nd) * kTileD;
+  const unsigned r = id / nd;
+  const unsigned txy = r % tiles_xy;
+  const int b = (int)(r / tiles_xy);
+  const int x0 = (int)(txy % tiles_x) * kTileW, y0 = (int)(txy / tiles_x) * kTileH;
   const int rx = row & (kTileW - 1), ry = (row >> 4) & (kTileH - 1), dd = row >> 5;
-  tr.b = t.b;
-  tr.d = min(t.d0 + dd, D - 1);
-  tr.active = (t.x0 + rx < W) && (t.y0 + ry < H) && (t.d0 + dd < D);
-  const int ox = min(t.x0 + rx, W - 1), oy = min(t.y0 + ry, H - 1);
-  tr.p = oy * W + ox;
+  const int d = min(d0 + dd, D - 1);
+  const bool active = (x0 + rx < W) && (y0 + ry < H) && (d0 + dd < D);
+  const int ox = min(x0 + rx, W - 1), oy = min(y0 + ry, H - 1);
+  const int p = oy * W + ox;
+  rc.b = b;
+  rc.out = active ? ((long long)b * D + d) * HW + p : -1;
+  rc.last_plane = (d == D - 1);
   const float pxc = (float)ox + 0.5f, pyc = (float)oy + 0.5f;
-  RowCtx& rc = tr.rc;
-  rc.dval = PER_PIXEL ? __ldg(planes + ((size_t)t.b * D + tr.d) * HW + tr.p) : __ldg(planes + t.b * D + tr.d);
+  rc.dval = PER_PIXEL ? __ldg(planes + ((size_t)b * D + d) * HW + p) : __ldg(planes + b * D + d);
   rc.dxc = pxc - ctr.half_w;
   rc.dyc = pyc - ctr.half_h;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) rc.cur4[j] = __ldg(cur4g + ((size_t)b * 4 + j) * HW + p);
   // rays: X = d * (invK3 p); n_cur = X / max(|X|, 1e-12)
-  const FrameParams& fp = frames[t.b];
-  const float rxv = fmaf(fp.invK[0], pxc, fmaf(fp.invK[1], pyc, fp.invK[2]));
-  const float ryv = fmaf(fp.invK[3], pxc, fmaf(fp.invK[4], pyc, fp.invK[5]));
-  const float rzv = fmaf(fp.invK[6], pxc, fmaf(fp.invK[7], pyc, fp.invK[8]));
+  const float4* fp = reinterpret_cast<const float4*>(frames + b);
+  const float4 k0 = __ldg(fp), k1 = __ldg(fp + 1);
+  const float k8 = __ldg(reinterpret_cast<const float*>(fp + 2));
+  const float rxv = fmaf(k0.x, pxc, fmaf(k0.y, pyc, k0.z));
+  const float ryv = fmaf(k0.w, pxc, fmaf(k1.x, pyc, k1.y));
+  const float rzv = fmaf(k1.z, pxc, fmaf(k1.w, pyc, k8));
   rc.X = rc.dval * rxv; rc.Y = rc.dval * ryv; rc.Z = rc.dval * rzv;
   const float ic = inv_norm(fmaf(rc.X, rc.X, fmaf(rc.Y, rc.Y, rc.Z * rc.Z)), kEpsNorm);
-  tr.cx = rc.X * ic; tr.cy = rc.Y * ic; tr.cz = rc.Z * ic;
-  const float i1 = inv_norm(fmaf(tr.cx, tr.cx, fmaf(tr.cy, tr.cy, tr.cz * tr.cz)), kEpsCos);
-  rc.cxn = tr.cx * i1; rc.cyn = tr.cy * i1; rc.czn = tr.cz * i1;
+  rc.cx = rc.X * ic; rc.cy = rc.Y * ic; rc.cz = rc.Z * ic;
+  const float i1 = inv_norm(fmaf(rc.cx, rc.cx, fmaf(rc.cy, rc.cy, rc.cz * rc.cz)), kEpsCos);
+  rc.cxn = rc.cx * i1; rc.cyn = rc.cy * i1; rc.czn = rc.cz * i1;
 }
 
 // K block `blk` (0..6: source view, 7: view-independent tail) of a row -> packed (hi, lo)
 template <int TW, int HWC>
-__device__ __forceinline__ unsigned build_block(TileRow& tr, int blk, const float4* __restrict__ cur4g,
-                                                const float4* __restrict__ src4,
+__device__ __forceinline__ unsigned build_block(const RowCtx& rc, int blk, const float4* __restrict__ src4,
                                                 const ViewParams* __restrict__ views, int W, int H, int HW,
-                                                const Centre& ctr, uint32_t (&hi)[13], uint32_t (&lo)[13]) {
-  float v[kBlk];
-  unsigned bits = 0;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) tr.rc.cur4[j] = __ldg(cur4g + ((size_t)tr.b * 4 + j) * HW + tr.p);
-  if (blk < kViews) {
-    bits = view_block<TW, HWC>(tr.rc, views[tr.b * kViews + blk],
-                               src4 + ((size_t)(tr.b * kViews + blk) * 4) * HW, W, H, HW, ctr, v);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      v[4 * j] = tr.rc.cur4[j].x; v[4 * j + 1] = tr.rc.cur4[j].y;
-      v[4 * j + 2] = tr.rc.cur4[j].z; v[4 * j + 3] = tr.rc.cur4[j].w;
-    }
-    v[kC] = tr.rc.dval; v[kC + 1] = tr.cx; v[kC + 2] = tr.cy; v[kC + 3] = tr.cz;
-#pragma unroll
-    for (int j = kC + 4; j < kBlk; ++j) v[j] = 0.f;
-  }
-  split_block(v, hi, lo);
-  return bits;
+                                                const Centre& ctr, bool want_bits, uint32_t (&hi)[13],
+                                                uint32_t (&lo)[13]) {
+  if (blk < kViews)
+    return view_block<TW, HWC>(rc, views + (rc.b * kViews + blk),
+                               src4 + ((size_t)(rc.b * kViews + blk) * 4) * HW, W, H, HW, ctr, want_bits, hi, lo);
+  tail_block(rc, hi, lo);
+  return 0u;
 }
 
 template <bool PER_PIXEL, int TW, int TH>
@@ -378,44 +382,38 @@ __global__ void __launch_bounds__(kThreads, 1)
 mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __restrict__ src4,
               const ViewParams* __restrict__ views, const FrameParams* __restrict__ frames,
               const float* __restrict__ planes, const uint8_t* __restrict__ image,
-              float* __restrict__ cost, uint8_t* __restrict__ mask_out, long long num_tiles) {
+              float* __restrict__ cost, uint8_t* __restrict__ mask_out, unsigned num_tiles) {
   SRCV_DYNAMIC_SMEM_ALIGNED(uint8_t, smem, 1024);
   __shared__ uint32_t s_tmem_base;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  uint64_t* bar_a1_full = bars + 0;   // workers -> MMA: A1 of a tile is in TMEM      (512 arrivals)
-  uint64_t* bar_mma1 = bars + 1;      // layer-1 MMAs done                           (commit)
-  uint64_t* bar_a2_full = bars + 2;   // workers -> MMA: A2 written, D1 consumed      (512 arrivals)
-  uint64_t* bar_mma2 = bars + 3;      // layer-2 MMAs done                           (commit)
-  uint64_t* bar_d_free = bars + 4;    // workers done reading the accumulator        (512 arrivals)
-  uint64_t* bar_e2 = bars + 5;        // layer-3 partial dots are in shared memory   (512 arrivals)
+  uint64_t* bar_a1_full = bars + 0;   // workers -> MMA: A1 of a tile is in TMEM               (512 arrivals)
+  uint64_t* bar_mma1 = bars + 1;      // layer-1 MMAs done: DA holds D1, A1 is free           (commit)
+  uint64_t* bar_a2_full = bars + 2;   // workers -> MMA: A2 written over D1                   (512 arrivals)
+  uint64_t* bar_mma2 = bars + 3;      // layer-2 MMAs done: D2 ready, DA free                 (commit)
+  uint64_t* bar_d2_free = bars + 4;   // workers done reading D2                              (512 arrivals)
+  uint64_t* bar_e2 = bars + 5;        // layer-3 partial dots are in shared memory            (512 arrivals)
+  uint64_t* bar_img = bars + 6;       // weight image landed in shared memory (bulk copies)
   uint8_t* sflag = smem + kOffFlag;
   float* spart = reinterpret_cast<float*>(smem + kOffPart);
   const float* svec = reinterpret_cast<const float*>(smem + kOffVec);
 
-  // SRCV_TC_UNIFORM_WARP (round-2 experiment, off by default): taking the warp index through a
-  // shuffle broadcast tells ptxas the role branches below are warp-uniform, so the global-memory
-  // descriptor stays in uniform registers instead of being re-materialised with two R2UR before
-  // every LDG of the worker loop (static SASS of the 160x120 kernel: 441 -> 59 R2UR, 3784 -> 3464
-  // instructions, spill stores 82 -> 54 bytes).  Same value on every lane either way; not yet
-  // run on a GPU, hence not the default.
-#ifdef SRCV_TC_UNIFORM_WARP
+  // The warp index goes through a shuffle broadcast so that ptxas knows the role branches are
+  // warp-uniform and keeps the global-memory descriptors in uniform registers.
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
-#else
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-#endif
   const int W = TW ? TW : s.W, H = TH ? TH : s.H, HW = W * H, D = s.D;
   constexpr int HWC = TW * TH;
-  const int tiles_x = (W + kTileW - 1) / kTileW, tiles_xy = tiles_x * ((H + kTileH - 1) / kTileH);
+  const unsigned tiles_x = (unsigned)(W + kTileW - 1) / kTileW;
+  const unsigned tiles_xy = tiles_x * ((unsigned)(H + kTileH - 1) / kTileH);
+  const unsigned nd = (unsigned)(D + kTileD - 1) / kTileD;
 
   // ---- one-time setup ----------------------------------------------------------------
-  uint64_t* bar_img = bars + 6;       // weight image landed in shared memory (bulk copies)
   if (tid == 0) {
     mbar_init(bar_img, 1);
     mbar_init(bar_a1_full, kWorkers);
     mbar_init(bar_mma1, 1);
     mbar_init(bar_a2_full, kWorkers);
     mbar_init(bar_mma2, 1);
-    mbar_init(bar_d_free, kWorkers);
+    mbar_init(bar_d2_free, kWorkers);
     mbar_init(bar_e2, kWorkers);
     mbar_fence_init();
   }
@@ -437,61 +435,71 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
   const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   // Work split: CTA c takes tiles c, c + grid, c + 2 grid, ... of the plane-fastest tile
   // order, i.e. at any moment the 148 CTAs sweep ~2 neighbouring pixel blocks x 64 planes of
-  // ONE frame, whose source features (39 MB) stay L2-resident.  (Measured alternatives: one
-  // contiguous range per CTA over the whole batch 2.98 ms, per frame 3.02 ms vs 2.71 ms for
-  // this interleaving at B = 8.)  Local index j -> tile id.
-  const long long tile_begin = 0;
-  const long long tile_end = (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-  auto tile_id = [&](long long j) { return (long long)blockIdx.x + j * gridDim.x; };
+  // ONE frame, whose source features (39 MB) stay L2-resident, and every CTA sees the same mix
+  // of interior and border patches.
+  const unsigned n_local = (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  auto tile_id = [&](unsigned j) { return blockIdx.x + j * gridDim.x; };
 
   if (warp < kWorkWarps) {
     // =============================== row workers =========================================
+    reg_inc<kRegsWorker>();
     const int row = tid & (kRows - 1), q = tid >> 7;
     const Centre ctr(W, H);
     const int blk0 = 2 * q, blk1 = 2 * q + 1;   // q = 3: view 6 and the tail block (7)
-    TileRow cur_row, nxt_row;
+    const bool masks = mask_out != nullptr;
+    RowCtx rc;
     uint32_t hi[13], lo[13];
-    long long id = tile_begin;
-    if (id < tile_end) {
+    long long out_cur = -1;
+    bool last_cur = false;
+    if (n_local > 0) {
       // prologue: the first tile's A operand (its columns are free)
-      make_tile_row<PER_PIXEL>(tile_id(id), row, W, H, HW, D, tiles_x, tiles_xy, ctr, frames, planes, cur_row);
-      unsigned bits = build_block<TW, HWC>(cur_row, blk0, cur4g, src4, views, W, H, HW, ctr, hi, lo);
+      make_row<PER_PIXEL>(tile_id(0), row, W, H, HW, D, nd, tiles_x, tiles_xy, ctr, cur4g, frames, planes, rc);
+      const bool wb = masks && rc.last_plane;
+      unsigned bits = build_block<TW, HWC>(rc, blk0, src4, views, W, H, HW, ctr, wb, hi, lo);
       store_block(lane_base, (uint32_t)(13 * blk0), hi, lo);
-      bits |= build_block<TW, HWC>(cur_row, blk1, cur4g, src4, views, W, H, HW, ctr, hi, lo);
+      bits |= build_block<TW, HWC>(rc, blk1, src4, views, W, H, HW, ctr, wb, hi, lo);
       store_block(lane_base, (uint32_t)(13 * blk1), hi, lo);
-      sflag[(0 * 4 + q) * kRows + row] = (uint8_t)bits;
+      if (wb) sflag[(0 * 4 + q) * kRows + row] = (uint8_t)bits;
       wait_st();
       fence_before_sync();
       mbar_arrive(bar_a1_full);
+      out_cur = rc.out;
+      last_cur = rc.last_plane;
     }
-    int it = 0;
-    for (; id < tile_end; ++id, ++it) {
-      const long long nid = id + 1;
-      const bool has_next = nid < tile_end;
+    for (unsigned it = 0; it < n_local; ++it) {
+      const uint32_t par = it & 1u;
+      const bool has_next = it + 1 < n_local;
       unsigned nbits = 0;
+      bool nwb = false;
       if (has_next) {
         // first K block of the NEXT tile, built while this tile's layer-1 MMAs run
-        make_tile_row<PER_PIXEL>(tile_id(nid), row, W, H, HW, D, tiles_x, tiles_xy, ctr, frames, planes, nxt_row);
-        nbits = build_block<TW, HWC>(nxt_row, blk0, cur4g, src4, views, W, H, HW, ctr, hi, lo);
+        make_row<PER_PIXEL>(tile_id(it + 1), row, W, H, HW, D, nd, tiles_x, tiles_xy, ctr, cur4g, frames, planes, rc);
+        nwb = masks && rc.last_plane;
+        nbits = build_block<TW, HWC>(rc, blk0, src4, views, W, H, HW, ctr, nwb, hi, lo);
       }
-      // ---- layer-1 epilogue on columns [32q, 32q+32): bias + LeakyReLU, (hi, lo), A2 -> TMEM
-      mbar_wait(bar_mma1, it & 1);
+      // ---- layer-1 epilogue on columns [32q, 32q+32): LeakyReLU, (hi, lo), A2 IN PLACE
+      mbar_wait(bar_mma1, par);
       fence_after_sync();
-#pragma unroll
-      for (int c0 = 32 * q; c0 < 32 * q + 32; c0 += 16) {
-        uint32_t r[16];
-        ld_x16(lane_base + kColD + c0, r);
+      // Mask bits of THIS tile.  The four quarters wrote them before their bar_a1_full arrival,
+      // so they are visible once bar_mma1 has completed; read here — before this thread's own
+      // bar_a1_full arrival for the next tile — the read is ordered before the store of the tile
+      // after next into the same parity slot (that store follows a bar_mma1 wait whose MMAs
+      // need every worker's bar_a1_full arrival).
+      unsigned tile_bits = 0;
+      if (q == 0 && masks && last_cur) {
+        const uint8_t* fl = sflag + par * 4 * kRows + row;
+        tile_bits = fl[0] | fl[kRows] | fl[2 * kRows] | fl[3 * kRows];
+      }
+      {
+        uint32_t r[32];
+        ld_x32(lane_base + kColDA + 32 * q, r);
         wait_ld();
-        uint32_t ehi[8], elo[8];
+        uint32_t ehi[16], elo[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float2 bb = *reinterpret_cast<const float2*>(svec + c0 + 2 * j);
-          const float a = leaky(fmaf(__uint_as_float(r[2 * j]), kWUnscale, bb.x));
-          const float b = leaky(fmaf(__uint_as_float(r[2 * j + 1]), kWUnscale, bb.y));
-          split_pack(a, b, ehi[j], elo[j]);
-        }
-        st_x8(lane_base + kColA2Hi + c0 / 2, ehi);
-        st_x8(lane_base + kColA2Lo + c0 / 2, elo);
+        for (int j = 0; j < 16; ++j)
+          split_pack(leaky(__uint_as_float(r[2 * j])), leaky(__uint_as_float(r[2 * j + 1])), ehi[j], elo[j]);
+        st_x16(lane_base + kColDA + 32 * q, ehi);
+        st_x16(lane_base + kColDA + 32 * q + 16, elo);
       }
       wait_st();
       fence_before_sync();
@@ -499,90 +507,85 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
       // ---- the rest of the next tile's A operand (A1 is free: layer 1 of this tile is done)
       if (has_next) {
         store_block(lane_base, (uint32_t)(13 * blk0), hi, lo);
-        nbits |= build_block<TW, HWC>(nxt_row, blk1, cur4g, src4, views, W, H, HW, ctr, hi, lo);
+        nbits |= build_block<TW, HWC>(rc, blk1, src4, views, W, H, HW, ctr, nwb, hi, lo);
         store_block(lane_base, (uint32_t)(13 * blk1), hi, lo);
-        sflag[(((it + 1) & 1) * 4 + q) * kRows + row] = (uint8_t)nbits;
+        if (nwb) sflag[((par ^ 1u) * 4 + q) * kRows + row] = (uint8_t)nbits;
         wait_st();
         fence_before_sync();
         mbar_arrive(bar_a1_full);
       }
       // ---- layer-2 epilogue on columns [32q, 32q+32): bias + LeakyReLU, 128 -> 1 partial dot
-      mbar_wait(bar_mma2, it & 1);
+      mbar_wait(bar_mma2, par);
       fence_after_sync();
-      float acc = 0.f;
-#pragma unroll
-      for (int c0 = 32 * q; c0 < 32 * q + 32; c0 += 16) {
-        uint32_t r[16];
-        ld_x16(lane_base + kColD + c0, r);
+      float acc0 = 0.f, acc1 = 0.f;
+      {
+        uint32_t r[32];
+        ld_x32(lane_base + kColD2 + 32 * q, r);
         wait_ld();
+        fence_before_sync();
+        mbar_arrive(bar_d2_free);     // D2 is in registers: the next tile's layer 2 may overwrite it
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const float4 bb = *reinterpret_cast<const float4*>(svec + kN + c0 + j);
-          const float4 ww = *reinterpret_cast<const float4*>(svec + 2 * kN + c0 + j);
-          acc = fmaf(leaky(fmaf(__uint_as_float(r[j + 0]), kWUnscale, bb.x)), ww.x, acc);
-          acc = fmaf(leaky(fmaf(__uint_as_float(r[j + 1]), kWUnscale, bb.y)), ww.y, acc);
-          acc = fmaf(leaky(fmaf(__uint_as_float(r[j + 2]), kWUnscale, bb.z)), ww.z, acc);
-          acc = fmaf(leaky(fmaf(__uint_as_float(r[j + 3]), kWUnscale, bb.w)), ww.w, acc);
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bb = *reinterpret_cast<const float4*>(svec + 32 * q + j);
+          const float4 wa = *reinterpret_cast<const float4*>(svec + kN + 32 * q + j);
+          const float4 wn = *reinterpret_cast<const float4*>(svec + 2 * kN + 32 * q + j);
+          const float h0 = fmaf(__uint_as_float(r[j + 0]), kUnscale2, bb.x);
+          const float h1 = fmaf(__uint_as_float(r[j + 1]), kUnscale2, bb.y);
+          const float h2 = fmaf(__uint_as_float(r[j + 2]), kUnscale2, bb.z);
+          const float h3 = fmaf(__uint_as_float(r[j + 3]), kUnscale2, bb.w);
+          acc0 = fmaf(wn.x, fabsf(h0), fmaf(wa.x, h0, acc0));
+          acc1 = fmaf(wn.y, fabsf(h1), fmaf(wa.y, h1, acc1));
+          acc0 = fmaf(wn.z, fabsf(h2), fmaf(wa.z, h2, acc0));
+          acc1 = fmaf(wn.w, fabsf(h3), fmaf(wa.w, h3, acc1));
         }
       }
-#ifdef SRCV_TC_EARLY_FLAGS
-      // Mask bits of THIS tile, read before the bar_d_free arrival.  The four quarters wrote them
-      // before their bar_a1_full arrival, so they are visible since the bar_mma1 wait above; read
-      // here, the read is ordered (d_free -> MMA issue -> bar_mma1 of the next tile) before the
-      // write of the tile after next into the same parity slot.  Read late (below, the default
-      // until this variant has run on a GPU) that write is unordered with the read: found by
-      // ThreadSanitizer on the host emulation; on hardware the reader would have to stall for a
-      // whole MMA + epilogue (> 3 k clocks) between two adjacent instructions to lose the race.
-      unsigned tile_bits = 0;
-      if (q == 0 && mask_out != nullptr && cur_row.d == D - 1) {
-        const uint8_t* fl = sflag + (it & 1) * 4 * kRows + row;
-        tile_bits = fl[0] | fl[kRows] | fl[2 * kRows] | fl[3 * kRows];
-      }
-#endif
-      fence_before_sync();
-      mbar_arrive(bar_d_free);
-      spart[((it & 1) * 4 + q) * kRows + row] = acc;
+      spart[(par * 4 + q) * kRows + row] = acc0 + acc1;
       mbar_arrive(bar_e2);
       if (q == 0) {
         // fixed-order reduction of the four quarters (deterministic), bias, store
-        mbar_wait(bar_e2, it & 1);
-        const float* sp = spart + (it & 1) * 4 * kRows + row;
+        mbar_wait(bar_e2, par);
+        const float* sp = spart + par * 4 * kRows + row;
         const float total = ((sp[0] + sp[kRows]) + sp[2 * kRows]) + sp[3 * kRows];
-        if (cur_row.active) {
-          cost[((size_t)cur_row.b * D + cur_row.d) * HW + cur_row.p] = total + svec[3 * kN];
-          if (mask_out != nullptr && cur_row.d == D - 1) {
-#ifdef SRCV_TC_EARLY_FLAGS
-            const unsigned bits = tile_bits;
-#else
-            const uint8_t* fl = sflag + (it & 1) * 4 * kRows + row;
-            const unsigned bits = fl[0] | fl[kRows] | fl[2 * kRows] | fl[3 * kRows];
-#endif
-            mask_out[(size_t)cur_row.b * HW + cur_row.p] = (bits == 3u) ? 1 : 0;
+        if (out_cur >= 0) {
+          cost[out_cur] = total + svec[3 * kN];
+          if (masks && last_cur) {
+            // overall mask of the LAST plane (reference :625-637): any view in front AND any view
+            // inside the 2-pixel border, independently
+            const long long bb = out_cur / ((long long)D * HW);
+            mask_out[bb * HW + (out_cur - (bb * D + (D - 1)) * HW)] = (tile_bits == 3u) ? 1 : 0;
           }
         }
       }
-      cur_row = nxt_row;
+      out_cur = rc.out;
+      last_cur = rc.last_plane;
     }
-  } else if (warp == kMmaWarp) {
-    // =============================== MMA issuer ==========================================
-    const uint32_t sbase = smem_u32(smem);
-    int it = 0;
-    for (long long id = tile_begin; id < tile_end; ++id, ++it) {
-      mbar_wait(bar_a1_full, it & 1);          // A1 of this tile is in TMEM
-      mbar_wait(bar_d_free, (it & 1) ^ 1);     // previous tile's accumulator has been read
-      fence_after_sync();
-      if (lane == 0) {
-        issue_layer<kK1 / 16>(tmem_base, kColA1Hi, kColA1Lo, sbase + kOffW1Hi, sbase + kOffW1Lo);
-        mma_commit(bar_mma1);
+  } else {
+    reg_dec<kRegsMma>();
+    if (warp == kMmaWarp) {
+      // =============================== MMA issuer ==========================================
+      const uint32_t sbase = smem_u32(smem);
+      for (unsigned it = 0; it < n_local; ++it) {
+        const uint32_t par = it & 1u;
+        mbar_wait(bar_a1_full, par);             // A1 of this tile is in TMEM
+        fence_after_sync();
+        // DA is free: the layer-2 MMAs of the previous tile (its last readers) were issued before
+        // these and the tensor pipe executes this thread's MMAs in order.
+        if (lane == 0) {
+          issue_layer<kK1 / 16, false>(tmem_base + kColDA, tmem_base + kColA1Hi, kColA1Lo - kColA1Hi,
+                                       sbase + kOffW1Hi, sbase + kOffW1Lo);
+          mma_commit(bar_mma1);
+        }
+        __syncwarp();
+        mbar_wait(bar_a2_full, par);             // A2 written over D1
+        mbar_wait(bar_d2_free, par ^ 1u);        // previous tile's D2 has been read
+        fence_after_sync();
+        if (lane == 0) {
+          issue_layer<kK2 / 16, true>(tmem_base + kColD2, tmem_base + kColDA, 16u,
+                                      sbase + kOffW2Hi, sbase + kOffW2Lo);
+          mma_commit(bar_mma2);
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      mbar_wait(bar_a2_full, it & 1);          // A2 written, accumulator columns consumed
-      fence_after_sync();
-      if (lane == 0) {
-        issue_layer<kK2 / 16>(tmem_base, kColA2Hi, kColA2Lo, sbase + kOffW2Hi, sbase + kOffW2Lo);
-        mma_commit(bar_mma2);
-      }
-      __syncwarp();
     }
   }
   // ---- teardown ---------------------------------------------------------------------------
@@ -682,21 +685,31 @@ bool mlp_tc_supported(const srcv_shape& s, const srcv_mlp_weights& w) {
 }
 
 size_t mlp_tc_extra_bytes() { return (kImageBytes + 255) & ~(size_t)255; }
+size_t mlp_tc_image_bytes() { return kImageBytes; }
+
+cudaError_t launch_mlp_tc_pack(const srcv_mlp_weights& w, void* image, cudaStream_t stream) {
+  SRCV_LAUNCH(tc_pack_kernel, 64, 256, 0, stream, w, reinterpret_cast<uint8_t*>(image));
+  note_launch();
+  return cudaGetLastError();
+}
 
 cudaError_t launch_mlp_tc(const srcv_shape& s, const float* cur, const Workspace& ws,
                           const float* planes, bool per_pixel, const srcv_mlp_weights& w, float* cost,
                           float* lowest, uint8_t* mask, cudaStream_t stream) {
-  uint8_t* image = reinterpret_cast<uint8_t*>(ws.extra);
-  SRCV_LAUNCH(tc_pack_kernel, 64, 256, 0, stream, w, image);
-  note_launch();
-  cudaError_t err = cudaGetLastError();
-  if (err != cudaSuccess) return err;
+  // the caller may hand over an image packed earlier (srcv_mlp_pack_weights): nothing to do per call
+  const uint8_t* image = reinterpret_cast<const uint8_t*>(w.packed_image);
+  cudaError_t err = cudaSuccess;
+  if (image == nullptr) {
+    err = launch_mlp_tc_pack(w, ws.extra, stream);
+    if (err != cudaSuccess) return err;
+    image = reinterpret_cast<const uint8_t*>(ws.extra);
+  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles_x = (s.W + kTileW - 1) / kTileW, tiles_y = (s.H + kTileH - 1) / kTileH;
   const long long num_tiles = (long long)s.B * ((s.D + kTileD - 1) / kTileD) * tiles_x * tiles_y;
-  if (num_tiles >= (1ll << 31)) return cudaErrorInvalidValue;   // tile ids are kept 32-bit-safe
+  if (num_tiles >= (1ll << 31)) return cudaErrorInvalidValue;   // tile ids are 32-bit
   const int grid = (int)(num_tiles < sms ? num_tiles : sms);
   const float4* src4 = reinterpret_cast<const float4*>(ws.src_c4);
   const float4* cur4 = reinterpret_cast<const float4*>(ws.cur_c4);
@@ -707,7 +720,7 @@ cudaError_t launch_mlp_tc(const srcv_shape& s, const float* cur, const Workspace
                                (int)kSmemBytes);                                                      \
     if (err != cudaSuccess) return err;                                                               \
     SRCV_LAUNCH((mlp_tc_kernel<PP, TW_, TH_>), grid, kThreads, kSmemBytes, stream,                    \
-                s, cur4, src4, ws.views, ws.frames, planes, image, cost, mask, num_tiles);            \
+                s, cur4, src4, ws.views, ws.frames, planes, image, cost, mask, (unsigned)num_tiles);  \
   } while (0)
 #define SRCV_TC_SIZES(PP)                                                   \
   if (s.W == 160 && s.H == 120) SRCV_TC_LAUNCH(PP, 160, 120);               \

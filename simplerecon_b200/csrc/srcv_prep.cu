@@ -10,6 +10,7 @@
 //    the fast kernels gather from: a bilinear tap is C/4 16-byte vector loads and
 //    horizontally adjacent pixels read adjacent vectors.
 #include "srcv_kernels.h"
+#include "srcv_tc.cuh"
 
 namespace srcv {
 
@@ -70,9 +71,11 @@ __device__ void view_params(const float* __restrict__ Kmat, const float* __restr
     out->rmeas = rm;
     out->tmeas = tm;
     out->comb = sqrtf(__fadd_rn(__fmul_rn(tm, tm), __fmul_rn(rm, rm)));
+    tc::split_pack(rm, tm, out->rt_hi, out->rt_lo);
   } else {
     out->centre[0] = out->centre[1] = out->centre[2] = 0.0f;
     out->rmeas = out->tmeas = out->comb = 0.0f;
+    out->rt_hi = out->rt_lo = 0u;
   }
 }
 
@@ -137,7 +140,8 @@ prep_kernel(srcv_shape s, srcv_cameras cams, srcv_planes pl, const float* __rest
   i -= nf;
   if (i < np) {
     const int d = (int)(i % s.D);
-    const float mn = *pl.min_depth, mx = *pl.max_depth;
+    const long long fb = pl.range_per_frame ? i / s.D : 0;   // one range for all frames, or one per frame
+    const float mn = pl.min_depth[fb], mx = pl.max_depth[fb];
     // exp(log(min) + log(max/min) * ramp): three separate torch ops in the reference
     const float v = expf(__fadd_rn(logf(mn), __fmul_rn(logf(__fdiv_rn(mx, mn)), pl.ramp[d])));
     planes_ws[i] = v;

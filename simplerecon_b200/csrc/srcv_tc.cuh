@@ -197,11 +197,19 @@ __device__ __forceinline__ uint32_t pack_f16x2_sat(float even, float odd) {
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(odd), "f"(even));  // {upper, lower}
   return d;
 }
+// The residual x - hi is one mixed-precision FMA per value (fma.rn.f32.f16: hi * (-1) + x, SASS
+// FHFMA with an .H0 / .H1 selector on the packed word) — four instructions per PAIR of values.
 __device__ __forceinline__ void split_pack(float even, float odd, uint32_t& hi, uint32_t& lo) {
   hi = pack_f16x2_sat(even, odd);
-  const __half2 h = *reinterpret_cast<const __half2*>(&hi);
-  const float2 back = __half22float2(h);
-  lo = pack_f16x2_sat(even - back.x, odd - back.y);
+  float re, ro;
+  asm("{\n\t.reg .b16 h0, h1, m1;\n\t"
+      "mov.b32 {h0, h1}, %2;\n\t"
+      "mov.b16 m1, 0xBC00;\n\t"               // -1.0 in fp16
+      "fma.rn.f32.f16 %0, h0, m1, %3;\n\t"
+      "fma.rn.f32.f16 %1, h1, m1, %4;\n\t}"
+      : "=f"(re), "=f"(ro)
+      : "r"(hi), "f"(even), "f"(odd));
+  lo = pack_f16x2_sat(re, ro);
 }
 
 }  // namespace tc

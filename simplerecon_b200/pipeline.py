@@ -26,14 +26,41 @@ class HostStreamer:
         self.s_run = torch.cuda.Stream(self.dev)
         self.s_out = torch.cuda.Stream(self.dev)
         self._host_out = [None, None]   # two pinned result sets, reused alternately
+        # Device-side input ring: three persistent slots (one being filled, one being swept, one
+        # whose sweep may still be in flight), allocated on first use and reused — no allocator
+        # call, no cross-stream record_stream bookkeeping per batch.
+        self._ring = [None, None, None]
+        self._ring_free = [None, None, None]   # event after which slot i may be overwritten
+        self._ring_next = 0
+
+    def _slot(self, host_batch: dict):
+        i = self._ring_next
+        self._ring_next = (i + 1) % len(self._ring)
+        slot = self._ring[i]
+        ok = slot is not None and slot.keys() == host_batch.keys() and all(
+            (not torch.is_tensor(v)) or (slot[k].shape == v.shape and slot[k].dtype == v.dtype)
+            for k, v in host_batch.items())
+        if not ok:
+            with torch.cuda.device(self.dev):
+                slot = {k: (torch.empty(v.shape, dtype=v.dtype, device=self.dev) if torch.is_tensor(v) else v)
+                        for k, v in host_batch.items()}
+            self._ring[i] = slot
+            self._ring_free[i] = None
+        return i, slot
 
     def _upload(self, host_batch: dict):
+        i, slot = self._slot(host_batch)
         with torch.cuda.stream(self.s_in):
-            dev = {k: (v.to(self.dev, non_blocking=True) if torch.is_tensor(v) else v)
-                   for k, v in host_batch.items()}
+            if self._ring_free[i] is not None:
+                self.s_in.wait_event(self._ring_free[i])      # the sweep that last read this slot is done
+            for k, v in host_batch.items():
+                if torch.is_tensor(v):
+                    slot[k].copy_(v, non_blocking=True)
+                else:
+                    slot[k] = v
             ev = torch.cuda.Event()
             ev.record(self.s_in)
-        return dev, ev
+        return (i, slot), ev
 
     def _download(self, results, slot: int, ev_done):
         keep = [t for t in (results[0], results[1], results[3]) if t is not None]
@@ -60,7 +87,7 @@ class HostStreamer:
         pending = None          # (host tensors, event) of the batch whose D2H is in flight
         slot = 0
         while nxt is not None:
-            dev_batch, ev_in = nxt
+            (ring_i, dev_batch), ev_in = nxt
             try:
                 nxt = self._upload(next(it))          # H2D of batch i+1 starts now
             except StopIteration:
@@ -68,11 +95,9 @@ class HostStreamer:
             with torch.cuda.stream(self.s_run):
                 self.s_run.wait_event(ev_in)
                 res = self.mgr(**dev_batch, return_mask=self.return_mask)
-                for v in dev_batch.values():
-                    if torch.is_tensor(v):
-                        v.record_stream(self.s_run)
                 ev_done = torch.cuda.Event()
                 ev_done.record(self.s_run)
+                self._ring_free[ring_i] = ev_done
             out = self._download(res, slot, ev_done)  # D2H of batch i
             if pending is not None:
                 pending[1].synchronize()

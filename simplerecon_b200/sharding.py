@@ -57,6 +57,28 @@ def init_distributed(backend: str | None = None) -> tuple[int, int, int]:
     return rank, world, local
 
 
+def bind_to_gpu_numa(local: int) -> list[int] | None:
+    """Pins this process to the CPUs NVML reports as local to GPU ``local`` (its NUMA node), so
+    that pinned staging buffers allocated afterwards are node-local and the cudaMemcpyAsync calls
+    of every rank do not cross the socket interconnect.  Returns the CPU list, or None when NVML
+    / affinity is unavailable (nothing is changed then).  Call before allocating pinned memory."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * wi + b for wi, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def barrier() -> None:
     if dist.is_initialized():
         dist.barrier()

@@ -24,11 +24,10 @@ def build(sanitize: str | None = None, force: bool = False) -> Path:
     out = BUILD / (f"libsrcv_emu_{sanitize}.so" if sanitize else "libsrcv_emu.so")
     if not force and out.is_file() and all(p.stat().st_mtime <= out.stat().st_mtime for p in SOURCES if p.is_file()):
         return out
-    # SRCV_TC_EARLY_FLAGS: the tcgen05 kernel with the mask-flag read moved before the bar_d_free
-    # arrival — the fix for the one (benign on hardware) unordered access ThreadSanitizer found in
-    # the default code; it becomes the nvcc default once it has run on a GPU.
-    # $SRCV_EMU_DEFINES overrides (e.g. "" to emulate exactly the shipped default).
-    defines = os.environ.get("SRCV_EMU_DEFINES", "-DSRCV_TC_EARLY_FLAGS").split()
+    # The emulation builds exactly the sources and switches the nvcc build ships (build.py
+    # NVCC_DEFINES); $SRCV_EMU_DEFINES adds experiment switches.
+    from simplerecon_b200.build import NVCC_DEFINES
+    defines = [*NVCC_DEFINES, *os.environ.get("SRCV_EMU_DEFINES", "").split()]
     flags = ["-std=c++20", "-pthread", "-fPIC", "-ffp-contract=off", "-DSRCV_HOST_EMU=1", *defines, f"-I{HERE}", "-w"]
     flags += ["-O1", "-g", f"-fsanitize={sanitize}"] if sanitize else ["-O2"]
     objs, procs = [], []

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(built_lib):
 
 
 def test_abi_version_and_status_strings(built_lib):
-    assert built_lib.srcv_abi_version() == 1
+    assert built_lib.srcv_abi_version() == 2
     assert built_lib.srcv_status_string(0) == b"ok"
     assert built_lib.srcv_status_string(2) == b"bad shape"
 

@@ -30,3 +30,20 @@ def test_algorithmic_bytes_match_survey():
     assert abs(bench.algorithmic_bytes_per_frame(CONFIGS[1], False, True) - 14.82e6) < 0.02e6
     assert abs(bench.algorithmic_bytes_per_frame(CONFIGS[2], True, True) - 14.84e6) < 0.02e6
     assert abs(bench.algorithmic_bytes_per_frame(CONFIGS[3], True, True) - 17.30e6) < 0.03e6
+
+
+def test_mlp_flops_match_survey_and_configs_agree_between_arms():
+    sys.path.insert(0, str(ROOT))
+    import bench
+    from simplerecon_b200.synthetic import CONFIGS
+    # 104.1 GFLOP (MLP) per frame at cfgA, 156.2 at cfgB
+    assert abs(bench.mlp_flops_per_frame(CONFIGS[2], False) - 104.1e9) < 0.1e9
+    assert abs(bench.mlp_flops_per_frame(CONFIGS[3], False) - 156.2e9) < 0.15e9
+    # what the tcgen05 kernel issues: 3 MMAs per product, K1 padded to 208
+    assert bench.mlp_flops_per_frame(CONFIGS[2], True) > 3 * 0.99 * bench.mlp_flops_per_frame(CONFIGS[2], False)
+    # the default workload is the hero configuration at 8 frames per GPU: N = 1 is BASELINE configs[2],
+    # N = 8 is configs[4]; both arms print the same `config`
+    assert bench.DEFAULT_WORKLOAD == "cfg2" and bench.PER_GPU["cfg2"] == 8
+    w = next(c for c in CONFIGS if c.name.startswith(bench.DEFAULT_WORKLOAD))
+    c1, _ = bench.workload_config(w, bench.PER_GPU["cfg2"], 8)
+    assert c1["global_batch"] == 64 and c1["matching"] == "mlp" and c1["planes"] == 64
