@@ -212,6 +212,41 @@ int32_t srcv_mlp_backward_f32(const srcv_shape* shape,
                               float* grad_cur, float* grad_src, const srcv_mlp_grads* grads,
                               void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- TSDF integration of depth maps (the consumer of the predicted depth) ---- *
+ * Replaces TSDFFuser.integrate_depth + project_to_camera (reference tools/tsdf.py:221-320,
+ * :204-219) as OurFuser.fuse_frames drives them (tools/fusers_helper.py:64-71): a dense
+ * (X,Y,Z) fp16 volume of truncated signed distances and running-average weights, z fastest,
+ * updated in place with a batch of depth maps applied IN ORDER.  All tensors are fp16, as in
+ * the reference (which `.half()`s depth, intrinsics and extrinsics): the arithmetic is the
+ * reference's op for op, every operation rounded to fp16.  One launch per <= 16 frames; a
+ * voxel's 4 bytes are read and written at most once per launch.
+ *   tsdf_values, tsdf_weights  DEVICE (X,Y,Z) fp16, updated in place (16-byte aligned and
+ *                              Z % 8 == 0 take the vector path; anything else a scalar path)
+ *   origin                     world position of voxel (0,0,0) (fp32, TSDF.from_bounds :85)
+ *   depth        DEVICE (B,H,W) fp16     cam_T_world, K  DEVICE (B,4,4) fp16
+ *   depth_mask   DEVICE (B,H,W) uint8 (0 = invalid pixel, :251-253) or NULL             */
+typedef struct srcv_tsdf_volume {
+  void* tsdf_values;
+  void* tsdf_weights;
+  int32_t X, Y, Z;
+  float origin[3];
+  float voxel_size;
+  float truncation_voxels; /* TSDFFuser.truncation_size (3.0), :181 */
+  float max_weight;        /* TSDFFuser.maxW (100.0), :182          */
+} srcv_tsdf_volume;
+typedef struct srcv_tsdf_frames {
+  const void* depth;
+  const void* cam_T_world;
+  const void* K;
+  const uint8_t* depth_mask;
+  int32_t B, H, W;
+  float min_depth; /* TSDFFuser(min_depth=0.5)  */
+  float max_depth; /* TSDFFuser(max_depth=5.0)  */
+} srcv_tsdf_frames;
+size_t srcv_tsdf_workspace_bytes(const srcv_tsdf_frames* frames);
+int32_t srcv_tsdf_integrate_f16(const srcv_tsdf_volume* volume, const srcv_tsdf_frames* frames,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- tuning / introspection ------------------------------------------- *
  * Selects the kernel variant used by the two forward calls on this thread's
  * next invocations (process-global).  0 = automatic choice.  Used by the tests

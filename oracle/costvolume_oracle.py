@@ -50,13 +50,16 @@ LRELU_SLOPE = 0.01    # nn.LeakyReLU() default, modules/networks.py:140
 # geometry                                                                    #
 # --------------------------------------------------------------------------- #
 def depth_planes(min_depth, max_depth, num_depth_bins: int, dtype=torch.float32, device=None):
-    """(D,) log-spaced plane depths.  modules/cost_volume.py:68-70, :124-127."""
-    min_depth = torch.as_tensor(min_depth, dtype=dtype, device=device).reshape(())
-    max_depth = torch.as_tensor(max_depth, dtype=dtype, device=device).reshape(())
+    """(D,) log-spaced plane depths — or (B,D) when the range holds one value per frame, which
+    the reference's expression broadcasts ((B,1,1,1) against the (1,D,1,1) ramp).
+    modules/cost_volume.py:68-70, :124-127."""
+    min_depth = torch.as_tensor(min_depth, dtype=dtype, device=device).reshape(-1)
+    max_depth = torch.as_tensor(max_depth, dtype=dtype, device=device).reshape(-1)
     # the reference builds the ramp in fp32 (register_buffer) and then .double()
     # converts the buffer, so an fp64 run still sees the fp32-rounded ramp.
     ramp = torch.linspace(0, 1, num_depth_bins).to(dtype).to(min_depth.device)
-    return torch.exp(torch.log(min_depth) + torch.log(max_depth / min_depth) * ramp)
+    out = torch.exp(torch.log(min_depth)[:, None] + torch.log(max_depth / min_depth)[:, None] * ramp[None])
+    return out[0] if out.shape[0] == 1 else out
 
 
 def pixel_centres(H: int, W: int, dtype=torch.float32, device=None):
@@ -152,7 +155,7 @@ def _planes_bdn(depth_planes_bdhw, min_depth, max_depth, B, D, H, W, dtype, devi
     """Returns (planes (B,D,N) view-able tensor, depth_planes_bdhw to hand back)."""
     if depth_planes_bdhw is None:
         d = depth_planes(min_depth, max_depth, D, dtype, device)
-        depth_planes_bdhw = d.view(1, D, 1, 1).expand(B, D, H, W)   # :129-134
+        depth_planes_bdhw = d.view(-1, D, 1, 1).expand(B, D, H, W)  # :129-134
     return depth_planes_bdhw.reshape(B, D, H * W), depth_planes_bdhw
 
 

@@ -104,3 +104,30 @@ def load_reference():
     )
     _cached = ns
     return ns
+
+
+_cached_tsdf = None
+
+
+def load_reference_tsdf():
+    """The reference's ``tools/tsdf.py`` (``TSDF``, ``TSDFFuser``) imported unmodified.  It
+    imports trimesh and skimage at module level (mesh export / marching cubes, not on the
+    integration path); neither is installed here, so inert stand-ins are registered."""
+    global _cached_tsdf
+    if _cached_tsdf is not None:
+        return _cached_tsdf
+    root = reference_root()
+    if root is None:
+        raise RuntimeError("reference tree not found (set $SIMPLERECON_REF or mount /root/reference)")
+    for name in ("trimesh", "skimage", "skimage.measure"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["skimage"].measure = sys.modules["skimage.measure"]
+    if not hasattr(sys.modules["trimesh"], "Trimesh"):
+        sys.modules["trimesh"].Trimesh = object
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_simplerecon_ref_tsdf", os.path.join(root, "tools", "tsdf.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    _cached_tsdf = types.SimpleNamespace(TSDF=mod.TSDF, TSDFFuser=mod.TSDFFuser, module=mod)
+    return _cached_tsdf

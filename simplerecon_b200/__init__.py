@@ -18,3 +18,4 @@ __all__ = [
     "BackprojectDepth", "Project3D", "pose_distance", "install", "uninstall",
 ]
 __version__ = "0.1.0"
+from .tsdf import TSDF, TSDFFuser  # noqa: E402,F401  (reference tools/tsdf.py)

@@ -52,6 +52,17 @@ class MlpGrads(C.Structure):
     _fields_ = [(n, _fp) for n in ("w1", "b1", "w2", "b2", "w3", "b3")]
 
 
+class TsdfVolume(C.Structure):
+    _fields_ = [("tsdf_values", _fp), ("tsdf_weights", _fp), ("X", C.c_int32), ("Y", C.c_int32), ("Z", C.c_int32),
+                ("origin", C.c_float * 3), ("voxel_size", C.c_float), ("truncation_voxels", C.c_float),
+                ("max_weight", C.c_float)]
+
+
+class TsdfFrames(C.Structure):
+    _fields_ = [("depth", _fp), ("cam_T_world", _fp), ("K", _fp), ("depth_mask", _fp), ("B", C.c_int32),
+                ("H", C.c_int32), ("W", C.c_int32), ("min_depth", C.c_float), ("max_depth", C.c_float)]
+
+
 # every symbol include/srcv_b200.h declares: (restype, argtypes)
 SYMBOLS = {
     "srcv_abi_version": (C.c_int32, []),
@@ -79,6 +90,8 @@ SYMBOLS = {
     "srcv_mlp_backward_f32": (C.c_int32, [C.POINTER(Shape), _fp, _fp, C.POINTER(Cameras), C.POINTER(Planes),
                                           C.POINTER(MlpWeights), _fp, _fp, _fp, C.POINTER(MlpGrads), _fp,
                                           C.c_size_t, _fp]),
+    "srcv_tsdf_workspace_bytes": (C.c_size_t, [C.POINTER(TsdfFrames)]),
+    "srcv_tsdf_integrate_f16": (C.c_int32, [C.POINTER(TsdfVolume), C.POINTER(TsdfFrames), _fp, C.c_size_t, _fp]),
     "srcv_set_variant": (C.c_int32, [C.c_int32]),
     "srcv_last_variant": (C.c_char_p, []),
     "srcv_launch_count": (C.c_uint64, []),

@@ -372,6 +372,33 @@ int32_t srcv_mlp_backward_f32(const srcv_shape* s, const float* cur, const float
   return SRCV_OK;
 }
 
+size_t srcv_tsdf_workspace_bytes(const srcv_tsdf_frames* f) {
+  if (!f || f->B <= 0) return 0;
+  return tsdf_workspace_bytes(f->B);
+}
+
+int32_t srcv_tsdf_integrate_f16(const srcv_tsdf_volume* v, const srcv_tsdf_frames* f, void* workspace,
+                                size_t workspace_bytes, void* stream_) {
+  if (!v || !f) return fail(SRCV_ERR_NULL, "volume / frames descriptor is NULL");
+  if (!v->tsdf_values || !v->tsdf_weights) return fail(SRCV_ERR_NULL, "tsdf_values / tsdf_weights is NULL");
+  if (!f->depth || !f->cam_T_world || !f->K) return fail(SRCV_ERR_NULL, "depth / cam_T_world / K is NULL");
+  if (v->X <= 0 || v->Y <= 0 || v->Z <= 0 || (long long)v->X * v->Y * v->Z > (1ll << 40))
+    return fail(SRCV_ERR_SHAPE, "bad volume dimensions %d x %d x %d", v->X, v->Y, v->Z);
+  if (f->B <= 0 || f->H <= 0 || f->W <= 0 || f->W > 2048 || f->H > 2048)
+    return fail(SRCV_ERR_SHAPE, "bad frame batch B=%d H=%d W=%d (image sizes up to 2048 are exact in fp16)", f->B, f->H, f->W);
+  if (!(v->voxel_size > 0.f) || !(v->truncation_voxels > 0.f) || !(v->max_weight > 0.f) || !(f->max_depth > f->min_depth))
+    return fail(SRCV_ERR_SHAPE, "voxel_size, truncation, max_weight must be positive and max_depth > min_depth");
+  if (((reinterpret_cast<uintptr_t>(v->tsdf_values) | reinterpret_cast<uintptr_t>(v->tsdf_weights) |
+        reinterpret_cast<uintptr_t>(f->depth) | reinterpret_cast<uintptr_t>(f->cam_T_world) |
+        reinterpret_cast<uintptr_t>(f->K)) & 1u) != 0)
+    return fail(SRCV_ERR_UNSUPPORTED, "fp16 arrays must be 2-byte aligned");
+  if (int32_t e = check_workspace(workspace, workspace_bytes, tsdf_workspace_bytes(f->B))) return e;
+  g_last_variant.store("tsdf_integrate_f16");
+  cudaError_t err = launch_tsdf_integrate(*v, *f, workspace, static_cast<cudaStream_t>(stream_));
+  if (err != cudaSuccess) return cuda_fail(err, "tsdf_integrate");
+  return SRCV_OK;
+}
+
 int32_t srcv_tc_selftest_f32(const float* A, const float* Wm, int32_t Kp, float* D, void* scratch,
                              void* stream) {
   if (!A || !Wm || !D || !scratch) return fail(SRCV_ERR_NULL, "selftest pointer is NULL");

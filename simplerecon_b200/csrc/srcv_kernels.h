@@ -93,6 +93,11 @@ cudaError_t launch_mlp_tc(const srcv_shape& s, const float* cur, const Workspace
 cudaError_t launch_tc_selftest(const float* A, const float* Wm, int Kp, float* Dout, void* scratch,
                                cudaStream_t stream);
 
+// dense-grid TSDF integration (csrc/srcv_tsdf.cu)
+size_t tsdf_workspace_bytes(int frames);
+cudaError_t launch_tsdf_integrate(const srcv_tsdf_volume& v, const srcv_tsdf_frames& f, void* workspace,
+                                  cudaStream_t stream);
+
 // argmax over planes -> plane depth (used by variants that do not fuse it)
 cudaError_t launch_argmax(const srcv_shape& s, const float* cost, const float* planes,
                           bool per_pixel, float* lowest, cudaStream_t stream);

@@ -437,12 +437,22 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
   // order, i.e. at any moment the 148 CTAs sweep ~2 neighbouring pixel blocks x 64 planes of
   // ONE frame, whose source features (39 MB) stay L2-resident, and every CTA sees the same mix
   // of interior and border patches.
+#ifdef SRCV_TC_CONTIG
+  // experiment switch: one contiguous tile range per CTA (consecutive plane chunks of a patch)
+  const unsigned t_lo = (unsigned)(((unsigned long long)num_tiles * blockIdx.x) / gridDim.x);
+  const unsigned t_hi = (unsigned)(((unsigned long long)num_tiles * (blockIdx.x + 1)) / gridDim.x);
+  const unsigned n_local = t_hi - t_lo;
+  auto tile_id = [&](unsigned j) { return t_lo + j; };
+#else
   const unsigned n_local = (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
   auto tile_id = [&](unsigned j) { return blockIdx.x + j * gridDim.x; };
+#endif
 
   if (warp < kWorkWarps) {
     // =============================== row workers =========================================
+#ifndef SRCV_TC_NO_SETMAXNREG
     reg_inc<kRegsWorker>();
+#endif
     const int row = tid & (kRows - 1), q = tid >> 7;
     const Centre ctr(W, H);
     const int blk0 = 2 * q, blk1 = 2 * q + 1;   // q = 3: view 6 and the tail block (7)
@@ -560,7 +570,9 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
       last_cur = rc.last_plane;
     }
   } else {
+#ifndef SRCV_TC_NO_SETMAXNREG
     reg_dec<kRegsMma>();
+#endif
     if (warp == kMmaWarp) {
       // =============================== MMA issuer ==========================================
       const uint32_t sbase = smem_u32(smem);

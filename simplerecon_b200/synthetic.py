@@ -156,3 +156,42 @@ def mlp_state(views: int = 7, channels: int = 16, hidden=(128, 128), seed: int =
 
 def to_device(tup: dict, device) -> dict:
     return {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in tup.items()}
+
+
+def make_tsdf_case(seed: int = 0, frames: int = 2, voxel_size: float = 0.04, height: int = 192, width: int = 256,
+                   room=(4.0, 3.0, 2.6), masked: bool = False) -> dict:
+    """A synthetic fusion step for the dense-grid TSDF integration (reference tools/tsdf.py:221-320):
+    `frames` depth maps of a box-shaped room seen from inside (ray-cast analytically, plus noise),
+    intrinsics of a ScanNet-like camera at (height, width), world->camera extrinsics, and the
+    volume bounds OurFuser would take from a mesh of that room (tools/tsdf.py:52-67)."""
+    g = torch.Generator().manual_seed(4321 + seed)
+    rx, ry, rz = room
+    fx = SCANNET_FX * width / 640.0
+    fy = SCANNET_FY * height / 480.0
+    K = torch.eye(4, dtype=torch.float64)
+    K[0, 0], K[1, 1], K[0, 2], K[1, 2] = fx, fy, SCANNET_CX * width / 640.0, SCANNET_CY * height / 480.0
+    v, u = torch.meshgrid(torch.arange(height, dtype=torch.float64) + 0.5,
+                          torch.arange(width, dtype=torch.float64) + 0.5, indexing="ij")
+    rays_cam = torch.stack([(u - K[0, 2]) / fx, (v - K[1, 2]) / fy, torch.ones_like(u)], -1)   # z = 1
+    depths, Es = [], []
+    for _ in range(frames):
+        pos = torch.tensor([rx, ry, rz], dtype=torch.float64) * (0.3 + 0.4 * torch.rand(3, generator=g, dtype=torch.float64))
+        axis = torch.randn(3, generator=g, dtype=torch.float64)
+        axis = axis / axis.norm()
+        Rwc = _axis_angle(axis[None], (torch.rand(1, generator=g, dtype=torch.float64) * 3.0))[0]   # camera -> world
+        d = rays_cam @ Rwc.T                                                 # ray directions in the world
+        lo, hi = -pos, torch.tensor([rx, ry, rz], dtype=torch.float64) - pos
+        t = torch.where(d > 0, hi / d.clamp_min(1e-12), lo / d.clamp_max(-1e-12))   # exit distance per axis
+        depth = t.min(-1).values                                            # along z = 1 rays: depth itself
+        depth = depth + 0.01 * torch.randn(depth.shape, generator=g, dtype=torch.float64)
+        depths.append(depth.float())
+        E = torch.eye(4, dtype=torch.float64)                                # world -> camera
+        E[:3, :3] = Rwc.T
+        E[:3, 3] = -(Rwc.T @ pos)
+        Es.append(E.float())
+    depth = torch.stack(depths)[:, None]
+    mask = (torch.rand(depth.shape, generator=g) > 0.1) if masked else None
+    pad = 3 * voxel_size
+    bounds = {"xmin": -pad, "xmax": rx + pad, "ymin": -pad, "ymax": ry + pad, "zmin": -pad, "zmax": rz + pad}
+    return dict(depth=depth, cam_T_world=torch.stack(Es), K=K.float().repeat(frames, 1, 1), mask=mask,
+                bounds=bounds, voxel_size=voxel_size, max_depth=3.0)

@@ -146,6 +146,7 @@ inline float __fadd_rn(float a, float b) { return a + b; }   // built with -ffp-
 inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fdiv_rn(float a, float b) { return a / b; }
 inline float __frcp_rn(float a) { return 1.0f / a; }
+inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 using std::max;
 using std::min;
 

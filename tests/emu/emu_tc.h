@@ -31,6 +31,7 @@ struct __half2 { __half x, y; };
 inline __half __float2half_rn(float f) { return __half{(_Float16)f}; }
 inline float __half2float(__half h) { return (float)h.v; }
 inline float2 __half22float2(__half2 h) { return make_float2((float)h.x.v, (float)h.y.v); }
+inline __half2 __floats2half2_rn(float a, float b) { return __half2{__half{(_Float16)a}, __half{(_Float16)b}}; }
 
 namespace srcv {
 namespace tc {

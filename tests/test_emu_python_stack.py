@@ -154,3 +154,79 @@ def test_warp_features_method(emulated):
     ref = O.sample_bilinear_zeros(t["src_feats"], px, py).reshape(B, K, C, H, W)
     assert (warped - ref).abs().max().item() <= 4e-5 * ref.abs().max().item() + 1e-6
     assert world.shape == (B * K, 4, H * W)
+
+
+@pytest.mark.parametrize("kind", ["dot", "mlp"])
+def test_training_with_strided_views_and_half_inputs(emulated, kind):
+    """(high) the reference caller passes VIEWS of one encoder output — cur_feats =
+    matching_feats[:, 0] is non-contiguous for B > 1 (experiment_modules/depth_model.py:242) — so
+    the backward must run on the dense copies the forward read; (medium) half / bf16 features
+    are upcast in the no-grad path exactly as in the autograd Functions."""
+    B, K, C, H, W, D = 2, 2, 8, 8, 10, 3
+    t = make_tuple(B, K, H, W, channels=C, seed=21)
+    g = torch.Generator().manual_seed(22)
+    feats = torch.randn(B, 1 + K, C, H, W, generator=g)
+    gcost = torch.randn(B, D, H, W, generator=g)
+    m = (S.CostVolumeManager(H, W, num_depth_bins=D) if kind == "dot" else _hero(K, C, H, W, D)).train()
+    fo = feats.clone().requires_grad_(True)
+    ours = dict(t)
+    ours["cur_feats"], ours["src_feats"] = fo[:, 0], fo[:, 1:]
+    assert not ours["cur_feats"].is_contiguous()
+    cost, *_ = m(**ours)
+    (cost * gcost).sum().backward()
+    f64 = feats.double().requires_grad_(True)
+    ref = {k: v.double() for k, v in t.items()}
+    ref["cur_feats"], ref["src_feats"] = f64[:, 0], f64[:, 1:]
+    if kind == "dot":
+        oc, *_ = O.forward_dot(**ref, num_depth_bins=D)
+    else:
+        wo = tuple(w.detach().double() for w in O.mlp_weights_from_state_dict(m.state_dict()))
+        oc, *_ = O.forward_mlp(**ref, weights=wo, num_depth_bins=D)
+    (oc * gcost.double()).sum().backward()
+    assert _rel(fo.grad, f64.grad) < 5e-5
+    # half inputs without grad (Lightning validation under autocast): upcast, same result as fp32 of the
+    # rounded values; with grad: gradients come back in the inputs' dtype
+    for dt in (torch.float16, torch.bfloat16):
+        fh = feats.to(dt)
+        with torch.no_grad():
+            ch, *_ = m(**{**t, "cur_feats": fh[:, 0], "src_feats": fh[:, 1:]})
+            cf, *_ = m(**{**t, "cur_feats": fh[:, 0].float(), "src_feats": fh[:, 1:].float()})
+        assert ch.dtype == torch.float32 and torch.equal(ch, cf)
+        fhg = fh.clone().requires_grad_(True)
+        cg, *_ = m(**{**t, "cur_feats": fhg[:, 0], "src_feats": fhg[:, 1:]})
+        (cg * gcost).sum().backward()
+        assert fhg.grad.dtype == dt and torch.isfinite(fhg.grad.float()).all()
+
+
+def test_unsupported_training_shape_fails_in_forward(emulated):
+    """The dot backward kernel serves C in {8, 16, 32}: a C = 4 training call is refused when the
+    graph is built, not at backward() time."""
+    B, K, C, H, W, D = 1, 2, 4, 6, 8, 3
+    t = make_tuple(B, K, H, W, channels=C, seed=23)
+    m = S.CostVolumeManager(H, W, num_depth_bins=D)
+    with torch.no_grad():
+        m(**t)                                  # inference is fine (generic kernel)
+    t["cur_feats"] = t["cur_feats"].clone().requires_grad_(True)
+    with pytest.raises(NotImplementedError):
+        m(**t)
+
+
+def test_per_frame_depth_range_and_weight_image_cache(emulated):
+    B, K, C, H, W, D = 2, 7, 16, 6, 16, 4
+    t = make_tuple(B, K, H, W, channels=C, seed=24)
+    t["min_depth"] = torch.tensor([0.25, 0.6]).view(B, 1, 1, 1)
+    t["max_depth"] = torch.tensor([5.0, 3.0]).view(B, 1, 1, 1)
+    m = _hero(K, C, H, W, D)
+    with torch.no_grad():
+        cost, lowest, planes, _ = m(**t)
+        key0 = m.__dict__["_srcv_packed"][0]
+        cost2, *_ = m(**t)
+        assert m.__dict__["_srcv_packed"][0] == key0 and torch.equal(cost, cost2)     # image reused
+        m.mlp.net[0].bias.add_(0.25)                                                  # in-place update: new version
+        cost3, *_ = m(**t)
+        assert m.__dict__["_srcv_packed"][0] != key0 and not torch.equal(cost3, cost)
+    assert "_srcv_packed" not in m.state_dict() and len(m.state_dict()) == 9
+    wts = O.mlp_weights_from_state_dict(m.state_dict())
+    oc, ol, op, _ = O.forward_mlp(**t, weights=wts, num_depth_bins=D)
+    assert torch.allclose(planes, op, rtol=3e-7, atol=0)
+    assert_cost_close("mlp", cost3, oc, what="per-frame range, tcgen05/emu")

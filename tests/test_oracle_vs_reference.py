@@ -74,3 +74,19 @@ def test_dot_gradients_match_live_reference_autograd():
         grads.append((tt["cur_feats"].grad, tt["src_feats"].grad))
     for a, b in zip(*grads):
         assert (a - b).abs().max().item() <= 2e-5 * float(a.abs().max()) + 1e-6
+
+
+def test_per_frame_depth_range_matches_live_reference():
+    """(B,1,1,1) min/max depth: the reference's generate_depth_planes broadcasts one range per
+    frame (modules/cost_volume.py:124-127); the oracle restates that."""
+    R = load_reference()
+    B, K, H, W, D = 3, 2, 10, 12, 5
+    t = make_tuple(B, K, H, W, seed=31)
+    t["min_depth"] = torch.tensor([0.25, 0.5, 0.3]).view(B, 1, 1, 1)
+    t["max_depth"] = torch.tensor([5.0, 8.0, 2.0]).view(B, 1, 1, 1)
+    ref = R.CostVolumeManager(H, W, num_depth_bins=D)
+    with torch.no_grad():
+        rc, rl, rp, _ = ref(**t)
+    oc, ol, op, _ = O.forward_dot(**t, num_depth_bins=D, sampler="aten")
+    assert torch.equal(op.contiguous(), rp.contiguous())
+    assert (oc - rc).abs().max().item() <= 2e-6 * float(rc.abs().max()) and torch.equal(ol, rl)
