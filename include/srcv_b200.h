@@ -162,6 +162,19 @@ int32_t srcv_warp_features_f32(const srcv_shape* shape, const float* src_feats,
                                int32_t per_pixel, float* warped, float* depths, float* mask,
                                void* workspace, size_t workspace_bytes, void* stream);
 
+/* All planes at once: replaces FastFeatureVolumeManager.warp_features (reference
+ * modules/cost_volume.py:812-964), which materialises the warped features of EVERY plane
+ * (550 MB per frame at the hero shape) — exported for callers of that method; the sweeps
+ * never call it.  shape->D = number of planes.
+ *   depth_planes DEVICE (B,D), or (B,D,H,W) when per_pixel != 0
+ *   warped (B,K,D,C,H,W)   depths, mask (B,K,D,H,W)
+ *   pix_coords (B,K,D,2,H,W): the projected pixel coordinates (x, y); NULL to skip        */
+int32_t srcv_warp_features_planes_f32(const srcv_shape* shape, const float* src_feats,
+                                      const srcv_cameras* cams, const float* depth_planes,
+                                      int32_t per_pixel, float* warped, float* depths, float* mask,
+                                      float* pix_coords, void* workspace, size_t workspace_bytes,
+                                      void* stream);
+
 /* ---- metadata-MLP volume ---------------------------------------------- *
  * Replaces FeatureVolumeManager.build_cost_volume /
  * FastFeatureVolumeManager.build_cost_volume + the argmax in forward

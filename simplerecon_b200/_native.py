@@ -79,6 +79,8 @@ SYMBOLS = {
     "srcv_warp_workspace_bytes": (C.c_size_t, [C.POINTER(Shape)]),
     "srcv_warp_features_f32": (C.c_int32, [C.POINTER(Shape), _fp, C.POINTER(Cameras), _fp, C.c_int32,
                                            _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
+    "srcv_warp_features_planes_f32": (C.c_int32, [C.POINTER(Shape), _fp, C.POINTER(Cameras), _fp, C.c_int32,
+                                                  _fp, _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
     "srcv_mlp_workspace_bytes": (C.c_size_t, [C.POINTER(Shape), C.POINTER(MlpWeights)]),
     "srcv_mlp_packed_bytes": (C.c_size_t, [C.POINTER(Shape), C.POINTER(MlpWeights)]),
     "srcv_mlp_pack_weights": (C.c_int32, [C.POINTER(Shape), C.POINTER(MlpWeights), _fp, _fp]),

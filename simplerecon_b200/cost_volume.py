@@ -522,3 +522,43 @@ class FastFeatureVolumeManager(FeatureVolumeManager):
                  mlp_channels=[202, 128, 128, 1], matching_dim_size=16, num_source_views=7):
         super().__init__(matching_height, matching_width, num_depth_bins, mlp_channels,
                          matching_dim_size, num_source_views)
+
+    # -- reference :812-964 ---------------------------------------------------
+    def warp_features(self, src_feats, src_extrinsics, src_Ks, cur_invK, depth_plane_bdhw,
+                      batch_size, num_src_frames, num_feat_channels, uv_scale=None):
+        """Warps every source view to the reference view at EVERY plane of ``depth_plane_bdhw``
+        and returns the reference's 5-tuple ``(world_points_bkd4hw, depths_bkdhw,
+        src_feat_warped_bkdfhw, mask_bkdhw, pix_coords_bkd2hw)``.  This is the materialising
+        form (550 MB per frame at the hero shape) the fused sweep avoids; it exists because the
+        reference exposes it.  ``uv_scale`` is accepted and unused (the kernel works in pixel
+        coordinates)."""
+        lib = _native.load()
+        dev = src_feats.device
+        _require_cuda(dev)
+        B, K, Cc = batch_size, num_src_frames, num_feat_channels
+        H, W = self.matching_height, self.matching_width
+        D = depth_plane_bdhw.shape[1]
+        src = _f32c(src_feats, "src_feats", dev).reshape(B, K, Cc, H, W)
+        E, Ks = _f32c(src_extrinsics, "src_extrinsics", dev), _f32c(src_Ks, "src_Ks", dev)
+        invK = _f32c(cur_invK, "cur_invK", dev)
+        st = depth_plane_bdhw.stride()
+        per_pixel = not ((st[2] == 0 or H == 1) and (st[3] == 0 or W == 1))
+        planes = _f32c(depth_plane_bdhw if per_pixel else depth_plane_bdhw[:, :, 0, 0], "depth_plane_bdhw", dev)
+        shape = _native.Shape(B, K, Cc, H, W, D)
+        cams = _native.Cameras(E.data_ptr(), None, Ks.data_ptr(), invK.data_ptr())
+        with torch.cuda.device(dev):
+            warped = torch.empty(B, K, D, Cc, H, W, device=dev, dtype=torch.float32)
+            depths = torch.empty(B, K, D, H, W, device=dev, dtype=torch.float32)
+            mask = torch.empty(B, K, D, H, W, device=dev, dtype=torch.float32)
+            pix = torch.empty(B, K, D, 2, H, W, device=dev, dtype=torch.float32)
+            n = lib.srcv_warp_workspace_bytes(C.byref(shape))
+            ws = torch.empty(n, device=dev, dtype=torch.uint8)
+            _native.check(lib.srcv_warp_features_planes_f32(
+                C.byref(shape), _ptr(src), C.byref(cams), _ptr(planes), int(per_pixel), _ptr(warped),
+                _ptr(depths), _ptr(mask), _ptr(pix), _ptr(ws), n,
+                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        # world points of every plane (:857-873): X = depth * (invK3 @ p), homogeneous
+        world = self.backprojector(depth_plane_bdhw.reshape(B * D, 1, H, W).expand(B * D, 1, H, W),
+                                   invK.repeat_interleave(D, dim=0))
+        world = world.reshape(B, 1, D, 4, H, W).expand(B, K, D, 4, H, W)
+        return world, depths, warped, mask, pix

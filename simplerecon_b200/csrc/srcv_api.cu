@@ -214,28 +214,48 @@ size_t srcv_warp_workspace_bytes(const srcv_shape* s) {
   return carve_workspace(*s, nullptr, false, 0).bytes;
 }
 
-int32_t srcv_warp_features_f32(const srcv_shape* s, const float* src, const srcv_cameras* cams,
-                               const float* depth_plane, int32_t per_pixel, float* warped,
-                               float* depths, float* mask, void* workspace, size_t workspace_bytes,
-                               void* stream_) {
+static int32_t warp_planes_impl(const srcv_shape* s, const float* src, const srcv_cameras* cams,
+                                const float* planes, int32_t per_pixel, float* warped, float* depths,
+                                float* mask, float* pix, void* workspace, size_t workspace_bytes,
+                                void* stream_) {
   if (int32_t e = check_shape(s)) return e;
-  if (!src || !depth_plane || !warped || !depths || !mask)
+  if (!src || !planes || !warped || !depths || !mask)
     return fail(SRCV_ERR_NULL, "warp_features pointer is NULL");
   if (!cams || !cams->src_extrinsics || !cams->src_Ks || !cams->cur_invK)
     return fail(SRCV_ERR_NULL, "camera block incomplete");
+  if (s->D > 65535) return fail(SRCV_ERR_SHAPE, "at most 65535 planes per warp call");
   const Workspace need = carve_workspace(*s, nullptr, false, 0);
   if (int32_t e = check_workspace(workspace, workspace_bytes, need.bytes)) return e;
   Workspace ws = carve_workspace(*s, workspace, false, 0);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   srcv_planes pl{};
-  pl.mode = SRCV_PLANES_PER_PLANE;   // the plane comes straight from the caller
-  pl.planes = depth_plane;
+  pl.mode = SRCV_PLANES_PER_PLANE;   // the planes come straight from the caller
+  pl.planes = planes;
   cudaError_t err = launch_prep(*s, *cams, pl, src, nullptr, ws, false, stream);
   if (err != cudaSuccess) return cuda_fail(err, "prep");
-  g_last_variant.store("warp_plane");
-  err = launch_warp_plane(*s, src, ws, depth_plane, per_pixel != 0, warped, depths, mask, stream);
+  g_last_variant.store("warp_planes");
+  err = launch_warp_planes(*s, src, ws, planes, per_pixel != 0, warped, depths, mask, pix, stream);
   if (err != cudaSuccess) return cuda_fail(err, g_last_variant.load());
   return SRCV_OK;
+}
+
+int32_t srcv_warp_features_f32(const srcv_shape* s, const float* src, const srcv_cameras* cams,
+                               const float* depth_plane, int32_t per_pixel, float* warped,
+                               float* depths, float* mask, void* workspace, size_t workspace_bytes,
+                               void* stream_) {
+  if (!s) return fail(SRCV_ERR_NULL, "shape is NULL");
+  srcv_shape one = *s;
+  one.D = 1;                         // shape->D is ignored: one plane
+  return warp_planes_impl(&one, src, cams, depth_plane, per_pixel, warped, depths, mask, nullptr, workspace,
+                          workspace_bytes, stream_);
+}
+
+int32_t srcv_warp_features_planes_f32(const srcv_shape* s, const float* src, const srcv_cameras* cams,
+                                      const float* depth_planes, int32_t per_pixel, float* warped,
+                                      float* depths, float* mask, float* pix_coords, void* workspace,
+                                      size_t workspace_bytes, void* stream_) {
+  return warp_planes_impl(s, src, cams, depth_planes, per_pixel, warped, depths, mask, pix_coords, workspace,
+                          workspace_bytes, stream_);
 }
 
 static int32_t check_weights(const srcv_shape* s, const srcv_mlp_weights* w) {

@@ -251,18 +251,22 @@ void launch_fast_sized(const srcv_shape& s, dim3 grid, dim3 block, size_t smem, 
 // --------------------------------------------------------------------------- //
 // warp only: the materialising helper the reference exposes as warp_features()  //
 // --------------------------------------------------------------------------- //
+// One thread per (frame, view, plane, pixel): grid.z walks the planes, so D = 1 is the reference's
+// single-plane CostVolumeManager.warp_features (modules/cost_volume.py:139-234) and D > 1 the
+// all-planes FastFeatureVolumeManager.warp_features (:812-964) — output layouts (B,K,D,C,H,W),
+// (B,K,D,H,W), and the un-centred pixel coordinates (B,K,D,2,H,W) the fast manager also returns.
 template <bool PER_PIXEL>
 __global__ void __launch_bounds__(128)
-warp_plane_kernel(srcv_shape s, const float* __restrict__ src, const ViewParams* __restrict__ views,
-                  const float* __restrict__ plane, float* __restrict__ warped,
-                  float* __restrict__ depths, float* __restrict__ mask) {
+warp_planes_kernel(srcv_shape s, const float* __restrict__ src, const ViewParams* __restrict__ views,
+                   const float* __restrict__ planes, float* __restrict__ warped,
+                   float* __restrict__ depths, float* __restrict__ mask, float* __restrict__ pix) {
   const int HW = s.H * s.W;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  const int bk = blockIdx.y, b = bk / s.K;
+  const int bk = blockIdx.y, b = bk / s.K, d = blockIdx.z;
   if (p >= HW) return;
   const Centre ctr(s.W, s.H);
   const float dx = ((float)(p % s.W) + 0.5f) - ctr.half_w, dy = ((float)(p / s.W) + 0.5f) - ctr.half_h;
-  const float dval = PER_PIXEL ? __ldg(plane + (size_t)b * HW + p) : __ldg(plane + b);
+  const float dval = PER_PIXEL ? __ldg(planes + ((size_t)b * s.D + d) * HW + p) : __ldg(planes + b * s.D + d);
   const ViewParams& vp = views[bk];
   float ax, ay, az, px, py, zp;
   homography_point(vp.a0, dx, dy, ax, ay, az);
@@ -272,6 +276,7 @@ warp_plane_kernel(srcv_shape s, const float* __restrict__ src, const ViewParams*
   const float w00 = (1.0f - tp.fx) * (1.0f - tp.fy), w01 = tp.fx * (1.0f - tp.fy);
   const float w10 = (1.0f - tp.fx) * tp.fy, w11 = tp.fx * tp.fy;
   const float* sp = src + (size_t)bk * s.C * HW + (tp.y0 * s.W + tp.x0);
+  const size_t o = (size_t)bk * s.D + d;
   for (int c = 0; c < s.C; ++c) {
     const float* q = sp + (size_t)c * HW;
     float v = 0.f;
@@ -279,20 +284,25 @@ warp_plane_kernel(srcv_shape s, const float* __restrict__ src, const ViewParams*
     if (tp.valid & 2u) v = fmaf(w01, __ldg(q + 1), v);
     if (tp.valid & 4u) v = fmaf(w10, __ldg(q + s.W), v);
     if (tp.valid & 8u) v = fmaf(w11, __ldg(q + s.W + 1), v);
-    warped[((size_t)bk * s.C + c) * HW + p] = v;
+    warped[(o * s.C + c) * HW + p] = v;
   }
-  depths[(size_t)bk * HW + p] = zp;
-  mask[(size_t)bk * HW + p] = zp > 0.0f ? 1.0f : 0.0f;
+  depths[o * HW + p] = zp;
+  mask[o * HW + p] = zp > 0.0f ? 1.0f : 0.0f;
+  if (pix != nullptr) {
+    // the projector's pixel coordinates (utils/geometry_utils.py:88-89): ours are centred
+    pix[(o * 2 + 0) * HW + p] = px + ((float)ctr.nx + 0.5f);
+    pix[(o * 2 + 1) * HW + p] = py + ((float)ctr.ny + 0.5f);
+  }
 }
 
 }  // namespace
 
-cudaError_t launch_warp_plane(const srcv_shape& s, const float* src, const Workspace& ws,
-                              const float* plane, bool per_pixel, float* warped, float* depths,
-                              float* mask, cudaStream_t stream) {
-  dim3 grid((s.H * s.W + 127) / 128, s.B * s.K), block(128);
-  if (per_pixel) SRCV_LAUNCH(warp_plane_kernel<true>, grid, block, 0, stream, s, src, ws.views, plane, warped, depths, mask);
-  else SRCV_LAUNCH(warp_plane_kernel<false>, grid, block, 0, stream, s, src, ws.views, plane, warped, depths, mask);
+cudaError_t launch_warp_planes(const srcv_shape& s, const float* src, const Workspace& ws,
+                               const float* planes, bool per_pixel, float* warped, float* depths,
+                               float* mask, float* pix, cudaStream_t stream) {
+  dim3 grid((s.H * s.W + 127) / 128, s.B * s.K, s.D), block(128);
+  if (per_pixel) SRCV_LAUNCH(warp_planes_kernel<true>, grid, block, 0, stream, s, src, ws.views, planes, warped, depths, mask, pix);
+  else SRCV_LAUNCH(warp_planes_kernel<false>, grid, block, 0, stream, s, src, ws.views, planes, warped, depths, mask, pix);
   note_launch();
   return cudaGetLastError();
 }

@@ -62,9 +62,9 @@ cudaError_t launch_dot_backward(const srcv_shape& s, const float* cur, const flo
                                 const float* gcost, float* gcur, float* gsrc, cudaStream_t stream);
 
 // single-plane warp (the reference's warp_features helper)
-cudaError_t launch_warp_plane(const srcv_shape& s, const float* src, const Workspace& ws,
-                              const float* plane, bool per_pixel, float* warped, float* depths,
-                              float* mask, cudaStream_t stream);
+cudaError_t launch_warp_planes(const srcv_shape& s, const float* src, const Workspace& ws,
+                               const float* planes, bool per_pixel, float* warped, float* depths,
+                               float* mask, float* pix, cudaStream_t stream);
 
 // metadata-MLP volume
 bool mlp_generic_supported(const srcv_shape& s, const srcv_mlp_weights& w);

@@ -143,3 +143,36 @@ def test_synthetic_tuples_are_deterministic_and_shaped():
     assert [(c.kind, c.batch, c.views, c.height, c.width, c.planes) for c in CONFIGS] == [
         ("dot", 1, 2, 48, 64, 16), ("dot", 4, 7, 120, 160, 64), ("mlp", 8, 7, 120, 160, 64),
         ("mlp", 16, 7, 120, 160, 96), ("mlp", 64, 7, 120, 160, 64)]
+
+
+def test_install_against_the_real_reference_module():
+    """install() on the UNMODIFIED reference's modules.cost_volume (build container only): the
+    three names resolve to our classes, `isinstance` / `to_fast()` as used by test.py:196-198 keep
+    working, a state_dict produced by the reference class loads strictly into ours, and
+    uninstall() restores the reference."""
+    from oracle.ref_import import load_reference, reference_available
+    if not reference_available():
+        pytest.skip("reference tree not mounted")
+    R = load_reference()
+    import modules.cost_volume as ref_cv          # importable once load_reference() put the tree on sys.path
+    orig = {n: getattr(ref_cv, n) for n in ("CostVolumeManager", "FeatureVolumeManager", "FastFeatureVolumeManager")}
+    ref_state = orig["FeatureVolumeManager"](12, 16, num_depth_bins=8, mlp_channels=[0, 128, 128, 1],
+                                             matching_dim_size=16, num_source_views=7).state_dict()
+    try:
+        patched = S.install()
+        assert "modules.cost_volume" in patched
+        assert ref_cv.CostVolumeManager is S.CostVolumeManager
+        assert ref_cv.FeatureVolumeManager is S.FeatureVolumeManager
+        assert ref_cv.FastFeatureVolumeManager is S.FastFeatureVolumeManager
+        # what experiment_modules/depth_model.py:162-176 does, by keyword
+        cv = ref_cv.FeatureVolumeManager(matching_height=12, matching_width=16, num_depth_bins=8,
+                                         matching_dim_size=16, num_source_views=7)
+        cv.load_state_dict(ref_state, strict=True)                     # Lightning loads strictly
+        assert isinstance(cv, ref_cv.FeatureVolumeManager)              # test.py:196
+        fast = cv.to_fast()                                             # test.py:198
+        assert isinstance(fast, ref_cv.FastFeatureVolumeManager) and fast.mlp is cv.mlp
+        assert set(cv.state_dict()) == set(ref_state)
+    finally:
+        S.uninstall()
+    for n, c in orig.items():
+        assert getattr(ref_cv, n) is c

@@ -230,3 +230,39 @@ def test_per_frame_depth_range_and_weight_image_cache(emulated):
     oc, ol, op, _ = O.forward_mlp(**t, weights=wts, num_depth_bins=D)
     assert torch.allclose(planes, op, rtol=3e-7, atol=0)
     assert_cost_close("mlp", cost3, oc, what="per-frame range, tcgen05/emu")
+
+
+def test_fast_manager_warp_features_five_tuple(emulated):
+    """FastFeatureVolumeManager.warp_features (reference modules/cost_volume.py:812-964): all planes
+    at once, 5-tuple (world points, depths, warped, mask, pixel coordinates) — against the oracle,
+    and against the live reference class where /root/reference is mounted."""
+    B, K, C, H, W, D = 2, 3, 8, 9, 12, 4
+    t = make_tuple(B, K, H, W, channels=C, seed=31)
+    m = _hero(K, C, H, W, D, fast=True)
+    planes = m.generate_depth_planes(B, t["min_depth"], t["max_depth"])
+    world, depths, warped, mask, pix = m.warp_features(t["src_feats"], t["src_extrinsics"], t["src_Ks"],
+                                                       t["cur_invK"], planes, B, K, C, None)
+    assert world.shape == (B, K, D, 4, H, W) and depths.shape == (B, K, D, H, W)
+    assert warped.shape == (B, K, D, C, H, W) and mask.shape == (B, K, D, H, W) and pix.shape == (B, K, D, 2, H, W)
+    rays = O.backproject_rays(t["cur_invK"], H, W)
+    for d in range(D):
+        X = planes[:, d, 0, 0].view(B, 1, 1) * rays
+        px, py, zp = O.project(X, t["src_Ks"], t["src_extrinsics"])
+        ref = O.sample_bilinear_zeros(t["src_feats"], px, py).reshape(B, K, C, H, W)
+        assert (warped[:, :, d] - ref).abs().max().item() <= 4e-5 * ref.abs().max().item() + 1e-6
+        assert torch.allclose(depths[:, :, d].reshape(B, K, -1), zp, rtol=2e-6, atol=1e-6)
+        assert torch.allclose(pix[:, :, d, 0].reshape(B, K, -1), px, rtol=0, atol=2e-4)
+        assert torch.allclose(pix[:, :, d, 1].reshape(B, K, -1), py, rtol=0, atol=2e-4)
+        assert torch.equal(mask[:, :, d].reshape(B, K, -1), (zp > 0).float())
+        assert torch.allclose(world[:, 0, d, :3].reshape(B, 3, -1), X, rtol=1e-6, atol=1e-7)
+    from oracle.ref_import import load_reference, reference_available
+    if reference_available():
+        R = load_reference()
+        ref = R.FastFeatureVolumeManager(H, W, num_depth_bins=D)
+        uv_scale = torch.tensor([1.0 / W, 1.0 / H]).view(1, 1, 1, 2)
+        with torch.no_grad():
+            rw, rd, rf, rm, rp = ref.warp_features(t["src_feats"], t["src_extrinsics"], t["src_Ks"], t["cur_invK"],
+                                                   planes, B, K, C, uv_scale)
+        assert torch.allclose(world, rw, rtol=1e-6, atol=1e-7) and torch.equal(mask, rm)
+        assert torch.allclose(depths, rd, rtol=2e-6, atol=1e-6) and torch.allclose(pix, rp, rtol=0, atol=2e-4)
+        assert (warped - rf).abs().max().item() <= 4e-5 * rf.abs().max().item() + 1e-6
