@@ -52,7 +52,19 @@ typedef struct srcv_shape {
   int32_t H; /* matching feature-map height                                  */
   int32_t W; /* matching feature-map width                                   */
   int32_t D; /* depth planes                                                 */
+  int32_t layout; /* srcv_feature_layout of cur_feats / src_feats (0 = the reference's NCHW)  */
 } srcv_shape;
+
+/* Memory layout of the two feature inputs.  CHUNK_PLANAR is what the gather kernels read
+ * internally — cur_feats (B,C/4,H,W,4), src_feats (B,K,C/4,H,W,4): a texel's 4-channel chunk is
+ * one 16-byte vector — and what srcv_instnorm_to_chunk_planar_f32 produces: a caller that
+ * hands it over skips the re-layout copy of the prep pass.  Served by the
+ * chunk-planar dot sweep (C == 16) and the tensor-core MLP sweep (K == 7, C == 16, 128/128);
+ * other shapes return SRCV_ERR_UNSUPPORTED.                                               */
+typedef enum srcv_feature_layout {
+  SRCV_LAYOUT_NCHW = 0,
+  SRCV_LAYOUT_CHUNK_PLANAR = 1
+} srcv_feature_layout;
 
 /* How the depth hypotheses are given. */
 typedef enum srcv_planes_mode {
@@ -88,6 +100,16 @@ typedef struct srcv_cameras {
   const float* src_poses;      /* (B,K,4,4) cur_cam_T_src_cam (MLP volume only; may be NULL for dot) */
   const float* src_Ks;         /* (B,K,4,4) source intrinsics at matching scale */
   const float* cur_invK;       /* (B,4,4) inverse intrinsics of the reference frame */
+  /* Optional raw poses.  When src_extrinsics is NULL the prep kernel forms
+   *   src_cam_T_cur_cam = src_cam_T_world @ cur_world_T_cam          (-> src_extrinsics)
+   *   cur_cam_T_src_cam = cur_cam_T_world @ src_world_T_cam          (-> src_poses)
+   * itself — the two batched 4x4 products experiment_modules/depth_model.py:324-332 runs in
+   * PyTorch before the call — evaluated in fp64 and rounded to fp32.  All four DEVICE pointers
+   * are then required ((B,K,4,4), (B,4,4), (B,4,4), (B,K,4,4)); ignored otherwise.        */
+  const float* src_cam_T_world;
+  const float* cur_world_T_cam;
+  const float* cur_cam_T_world;
+  const float* src_world_T_cam;
 } srcv_cameras;
 
 /* Weights of the matching MLP — the parameters of the reference's
@@ -224,6 +246,17 @@ int32_t srcv_mlp_backward_f32(const srcv_shape* shape,
                               const srcv_mlp_weights* weights, const float* grad_cost,
                               float* grad_cur, float* grad_src, const srcv_mlp_grads* grads,
                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- producer-side fusion: encoder tail -> chunk-planar features -------------------- *
+ * Replaces the last op of the reference's matching encoder, nn.InstanceNorm2d(C) without
+ * affine (modules/networks.py:201; biased variance), AND the re-layout pass of the sweeps:
+ *   x        DEVICE (B, V, C, H, W) fp32 — the conv output for the stacked (reference frame,
+ *            K = V-1 source views) images, as depth_model.py:220-243 produces it
+ *   cur_c4   DEVICE (B, C/4, H, W, 4)        normalised features of view 0
+ *   src_c4   DEVICE (B, V-1, C/4, H, W, 4)   normalised features of views 1..V-1
+ * Pass both to the forward calls with shape->layout = SRCV_LAYOUT_CHUNK_PLANAR.  C % 4 == 0. */
+int32_t srcv_instnorm_to_chunk_planar_f32(const float* x, int32_t B, int32_t V, int32_t C, int32_t H,
+                                          int32_t W, float eps, float* cur_c4, float* src_c4, void* stream);
 
 /* ---- TSDF integration of depth maps (the consumer of the predicted depth) ---- *
  * Replaces TSDFFuser.integrate_depth + project_to_camera (reference tools/tsdf.py:221-320,

@@ -7,7 +7,8 @@ reference's ``modules/cost_volume.py``, as hand-written sm_100a kernels in
 reference's manager classes that binds it.  Encoders, decoder, datasets and
 training stay the reference's own PyTorch code.
 """
-from .cost_volume import CostVolumeManager, FastFeatureVolumeManager, FeatureVolumeManager
+from .cost_volume import (CostVolumeManager, FastFeatureVolumeManager, FeatureVolumeManager,
+                          instance_norm_to_chunk_planar)
 from .geometry import BackprojectDepth, Project3D, pose_distance
 from .install import install, uninstall
 from .networks import MLP

@@ -14,6 +14,7 @@ PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "lib" / "libsrcv_b200.so"
 
 VARIANT_AUTO, VARIANT_GENERIC, VARIANT_FAST = 0, 1, 2
+LAYOUT_NCHW, LAYOUT_CHUNK_PLANAR = 0, 1
 PLANES_FROM_RANGE, PLANES_PER_PLANE, PLANES_PER_PIXEL = 0, 1, 2
 
 
@@ -31,7 +32,7 @@ _fp = C.c_void_p  # device pointers travel as plain addresses
 
 
 class Shape(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("B", "K", "C", "H", "W", "D")]
+    _fields_ = [(n, C.c_int32) for n in ("B", "K", "C", "H", "W", "D", "layout")]
 
 
 class Planes(C.Structure):
@@ -40,7 +41,9 @@ class Planes(C.Structure):
 
 
 class Cameras(C.Structure):
-    _fields_ = [("src_extrinsics", _fp), ("src_poses", _fp), ("src_Ks", _fp), ("cur_invK", _fp)]
+    _fields_ = [("src_extrinsics", _fp), ("src_poses", _fp), ("src_Ks", _fp), ("cur_invK", _fp),
+                ("src_cam_T_world", _fp), ("cur_world_T_cam", _fp), ("cur_cam_T_world", _fp),
+                ("src_world_T_cam", _fp)]
 
 
 class MlpWeights(C.Structure):
@@ -92,6 +95,8 @@ SYMBOLS = {
     "srcv_mlp_backward_f32": (C.c_int32, [C.POINTER(Shape), _fp, _fp, C.POINTER(Cameras), C.POINTER(Planes),
                                           C.POINTER(MlpWeights), _fp, _fp, _fp, C.POINTER(MlpGrads), _fp,
                                           C.c_size_t, _fp]),
+    "srcv_instnorm_to_chunk_planar_f32": (C.c_int32, [_fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                                      C.c_float, _fp, _fp, _fp]),
     "srcv_tsdf_workspace_bytes": (C.c_size_t, [C.POINTER(TsdfFrames)]),
     "srcv_tsdf_integrate_f16": (C.c_int32, [C.POINTER(TsdfVolume), C.POINTER(TsdfFrames), _fp, C.c_size_t, _fp]),
     "srcv_set_variant": (C.c_int32, [C.c_int32]),

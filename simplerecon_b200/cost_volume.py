@@ -71,6 +71,33 @@ def _check_backward_supported(kind: str, src_shape, hidden) -> None:
                 f"(K={K}, C={Cc}, hidden={tuple(hidden)})")
 
 
+def instance_norm_to_chunk_planar(x_bvchw: Tensor, eps: float = 1e-5):
+    """The matching encoder's final ``nn.InstanceNorm2d(C)`` (reference modules/networks.py:201:
+    no affine, biased variance, eps 1e-5) fused with the layout pass of the sweeps.
+
+    ``x_bvchw``: the conv output for the stacked images, ``(B, 1+K, C, H, W)`` (reference frame
+    first, as depth_model.py:220-243 arranges it).  Returns ``(cur_feats, src_feats)`` as
+    chunk-planar tensors ``(B,C/4,H,W,4)`` / ``(B,K,C/4,H,W,4)`` that the managers' ``forward``
+    accepts in place of the NCHW ones — the normalised NCHW tensor and the prep pass's re-layout
+    copy never exist."""
+    if not torch.is_tensor(x_bvchw) or x_bvchw.dim() != 5:
+        raise ValueError("expected a (B, 1+K, C, H, W) tensor")
+    dev = x_bvchw.device
+    _require_cuda(dev)
+    x = _f32c(x_bvchw, "x", dev)
+    B, V, Cc, H, W = x.shape
+    if Cc % 4 != 0:
+        raise ValueError("the chunk-planar layout needs C % 4 == 0")
+    lib = _native.load()
+    with torch.cuda.device(dev):
+        cur = torch.empty(B, Cc // 4, H, W, 4, device=dev, dtype=torch.float32)
+        src = torch.empty(B, max(V - 1, 0), Cc // 4, H, W, 4, device=dev, dtype=torch.float32)
+        _native.check(lib.srcv_instnorm_to_chunk_planar_f32(
+            _ptr(x), B, V, Cc, H, W, float(eps), _ptr(cur), _ptr(src) if V > 1 else C.c_void_p(0),
+            C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return cur, src
+
+
 class _DotVolumeFunction(torch.autograd.Function):
     """Differentiable wrapper of the dot-product sweep: fused forward, and a backward kernel
     (``srcv_dot_backward_f32``) for the two feature inputs — what autograd of the reference's
@@ -267,8 +294,20 @@ class CostVolumeManager(nn.Module):
     # shared argument handling
     # ------------------------------------------------------------------------
     def _prepare(self, cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK,
-                 min_depth, max_depth, depth_planes_bdhw, need_poses, allow_grad=False):
-        if not torch.is_tensor(src_feats) or src_feats.dim() != 5:
+                 min_depth, max_depth, depth_planes_bdhw, need_poses, allow_grad=False, raw_poses=None):
+        # chunk-planar features (B,K,C/4,H,W,4) / (B,C/4,H,W,4), e.g. from
+        # instance_norm_to_chunk_planar(): gathered in place, the prep pass makes no copy
+        chunk_planar = torch.is_tensor(src_feats) and src_feats.dim() == 6 and src_feats.shape[-1] == 4
+        if chunk_planar:
+            if cur_feats.dim() != 5 or cur_feats.shape[-1] != 4:
+                raise ValueError("chunk-planar src_feats (B,K,C/4,H,W,4) need chunk-planar cur_feats (B,C/4,H,W,4)")
+            if allow_grad or (torch.is_grad_enabled() and (cur_feats.requires_grad or src_feats.requires_grad)):
+                raise NotImplementedError("the backward kernels take the reference's NCHW features")
+            src_view = src_feats.permute(0, 1, 2, 5, 3, 4).flatten(2, 3)      # logical (B,K,C,H,W) view: shapes only
+            cur_view = cur_feats.permute(0, 1, 4, 2, 3).flatten(1, 2)
+        else:
+            src_view, cur_view = src_feats, cur_feats
+        if not torch.is_tensor(src_feats) or src_view.dim() != 5:
             raise ValueError("src_feats must be a (B,K,C,H,W) tensor")
         dev = src_feats.device
         _require_cuda(dev)
@@ -277,25 +316,36 @@ class CostVolumeManager(nn.Module):
                 or any(p.requires_grad for p in self.parameters())
         ):
             raise RuntimeError("internal: a gradient-requiring call reached the plain fused path")
-        B, K, Cc, H, W = src_feats.shape
+        B, K, Cc, H, W = src_view.shape
         if (H, W) != (self.matching_height, self.matching_width):
             raise ValueError(f"feature map {H}x{W} does not match the manager's "
                              f"{self.matching_height}x{self.matching_width}")
-        if tuple(cur_feats.shape) != (B, Cc, H, W):
-            raise ValueError(f"cur_feats shape {tuple(cur_feats.shape)} != {(B, Cc, H, W)}")
-        for name, t, shp in (("src_extrinsics", src_extrinsics, (B, K, 4, 4)),
-                             ("src_Ks", src_Ks, (B, K, 4, 4)),
-                             ("cur_invK", cur_invK, (B, 4, 4))):
-            if tuple(t.shape) != shp:
-                raise ValueError(f"{name} shape {tuple(t.shape)} != {shp}")
-        if need_poses and tuple(src_poses.shape) != (B, K, 4, 4):
-            raise ValueError(f"src_poses shape {tuple(src_poses.shape)} != {(B, K, 4, 4)}")
+        if tuple(cur_view.shape) != (B, Cc, H, W):
+            raise ValueError(f"cur_feats shape {tuple(cur_view.shape)} != {(B, Cc, H, W)}")
+        raw = raw_poses is not None
+        checks = [("src_Ks", src_Ks, (B, K, 4, 4)), ("cur_invK", cur_invK, (B, 4, 4))]
+        if raw:
+            # the prep kernel forms src_cam_T_cur_cam / cur_cam_T_src_cam itself (depth_model.py:324-332)
+            checks += [("src_cam_T_world", raw_poses["src_cam_T_world"], (B, K, 4, 4)),
+                       ("src_world_T_cam", raw_poses["src_world_T_cam"], (B, K, 4, 4)),
+                       ("cur_cam_T_world", raw_poses["cur_cam_T_world"], (B, 4, 4)),
+                       ("cur_world_T_cam", raw_poses["cur_world_T_cam"], (B, 4, 4))]
+        else:
+            checks.append(("src_extrinsics", src_extrinsics, (B, K, 4, 4)))
+            if need_poses:
+                checks.append(("src_poses", src_poses, (B, K, 4, 4)))
+        for name, tt, shp in checks:
+            if tuple(tt.shape) != shp:
+                raise ValueError(f"{name} shape {tuple(tt.shape)} != {shp}")
         t = dict(
             cur=_f32c(cur_feats, "cur_feats", dev), src=_f32c(src_feats, "src_feats", dev),
-            E=_f32c(src_extrinsics, "src_extrinsics", dev), Ks=_f32c(src_Ks, "src_Ks", dev),
+            E=None if raw else _f32c(src_extrinsics, "src_extrinsics", dev), Ks=_f32c(src_Ks, "src_Ks", dev),
             invK=_f32c(cur_invK, "cur_invK", dev),
-            poses=_f32c(src_poses, "src_poses", dev) if need_poses else None,
+            poses=_f32c(src_poses, "src_poses", dev) if (need_poses and not raw) else None,
         )
+        if raw:
+            for k in ("src_cam_T_world", "src_world_T_cam", "cur_cam_T_world", "cur_world_T_cam"):
+                t[k] = _f32c(raw_poses[k], k, dev)
         D = self.num_depth_bins
         pl = _native.Planes()
         keep = []
@@ -339,9 +389,15 @@ class CostVolumeManager(nn.Module):
             pl.min_depth = pl.max_depth = pl.ramp = pl.planes_out = None
             keep.append(per)
             planes_ret = depth_planes_bdhw
-        shape = _native.Shape(B, K, Cc, H, W, D)
-        cams = _native.Cameras(t["E"].data_ptr(), t["poses"].data_ptr() if need_poses else None,
-                               t["Ks"].data_ptr(), t["invK"].data_ptr())
+        shape = _native.Shape(B, K, Cc, H, W, D,
+                              _native.LAYOUT_CHUNK_PLANAR if chunk_planar else _native.LAYOUT_NCHW)
+        if raw:
+            cams = _native.Cameras(None, None, t["Ks"].data_ptr(), t["invK"].data_ptr(),
+                                   t["src_cam_T_world"].data_ptr(), t["cur_world_T_cam"].data_ptr(),
+                                   t["cur_cam_T_world"].data_ptr(), t["src_world_T_cam"].data_ptr())
+        else:
+            cams = _native.Cameras(t["E"].data_ptr(), t["poses"].data_ptr() if need_poses else None,
+                                   t["Ks"].data_ptr(), t["invK"].data_ptr())
         return dev, shape, t, cams, pl, planes_ret, keep
 
     # -- reference :237-335 ---------------------------------------------------
@@ -355,23 +411,25 @@ class CostVolumeManager(nn.Module):
         return cost, planes, mask
 
     def _run(self, cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK, min_depth,
-             max_depth, depth_planes_bdhw, return_mask, want_lowest):
+             max_depth, depth_planes_bdhw, return_mask, want_lowest, raw_poses=None):
         # `src_poses` and `return_mask` are ignored by the dot-product volume (:286)
         if torch.is_grad_enabled() and (cur_feats.requires_grad or src_feats.requires_grad):
+            if raw_poses is not None or cur_feats.dim() != 4:
+                raise NotImplementedError("raw_poses / chunk-planar features are inference-path options")
             # training: same fused forward, gradients w.r.t. the features by the backward kernel
             cost, lowest, planes_ret = _DotVolumeFunction.apply(
                 self, cur_feats, src_feats, src_extrinsics, src_Ks, cur_invK, min_depth, max_depth,
                 depth_planes_bdhw)
             return cost, (lowest if want_lowest else None), planes_ret, None
         return self._run_fused(cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK,
-                               min_depth, max_depth, depth_planes_bdhw, want_lowest)
+                               min_depth, max_depth, depth_planes_bdhw, want_lowest, raw_poses=raw_poses)
 
     def _run_fused(self, cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK, min_depth,
-                   max_depth, depth_planes_bdhw, want_lowest, allow_grad=False):
+                   max_depth, depth_planes_bdhw, want_lowest, allow_grad=False, raw_poses=None):
         lib = _native.load()
         dev, shape, t, cams, pl, planes_ret, keep = self._prepare(
             cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK, min_depth,
-            max_depth, depth_planes_bdhw, need_poses=False, allow_grad=allow_grad)
+            max_depth, depth_planes_bdhw, need_poses=False, allow_grad=allow_grad, raw_poses=raw_poses)
         with torch.cuda.device(dev):
             cost = torch.empty(shape.B, shape.D, shape.H, shape.W, device=dev, dtype=torch.float32)
             lowest = torch.empty(shape.B, shape.H, shape.W, device=dev, dtype=torch.float32) \
@@ -386,12 +444,20 @@ class CostVolumeManager(nn.Module):
 
     # -- reference :345-380 ---------------------------------------------------
     def forward(self, cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK,
-                min_depth, max_depth, depth_planes_bdhw=None, return_mask=False):
+                min_depth, max_depth, depth_planes_bdhw=None, return_mask=False, raw_poses=None):
         """Returns ``(cost_volume, lowest_cost, depth_planes_bdhw, overall_mask_bhw)``.
         ``lowest_cost`` is the plane depth at the ARGMAX of the volume, as in the
-        reference (:374-378)."""
+        reference (:374-378).
+
+        Two producer-side extensions beyond the reference's call, both optional:
+        ``cur_feats`` / ``src_feats`` may be CHUNK-PLANAR tensors ``(B,C/4,H,W,4)`` / ``(B,K,C/4,H,W,4)``
+        (``instance_norm_to_chunk_planar``), which the kernels gather in place; and ``raw_poses`` =
+        ``dict(src_cam_T_world, src_world_T_cam, cur_cam_T_world, cur_world_T_cam)`` makes the prep
+        kernel form the relative transforms of experiment_modules/depth_model.py:324-332 itself
+        (``src_extrinsics`` / ``src_poses`` are then ignored and may be None)."""
         return self._run(cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK,
-                         min_depth, max_depth, depth_planes_bdhw, return_mask, want_lowest=True)
+                         min_depth, max_depth, depth_planes_bdhw, return_mask, want_lowest=True,
+                         raw_poses=raw_poses)
 
 
 class FeatureVolumeManager(CostVolumeManager):
@@ -459,9 +525,11 @@ class FeatureVolumeManager(CostVolumeManager):
         return cache[1]
 
     def _run(self, cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK, min_depth,
-             max_depth, depth_planes_bdhw, return_mask, want_lowest):
+             max_depth, depth_planes_bdhw, return_mask, want_lowest, raw_poses=None):
         if torch.is_grad_enabled() and (cur_feats.requires_grad or src_feats.requires_grad
                                         or any(p.requires_grad for p in self.mlp.parameters())):
+            if raw_poses is not None or cur_feats.dim() != 4:
+                raise NotImplementedError("raw_poses / chunk-planar features are inference-path options")
             # training: same fused forward; gradients for features and MLP parameters by the
             # recompute backward kernel (srcv_mlp_backward_f32)
             lin = [m for m in self.mlp.net if isinstance(m, nn.Linear)]
@@ -473,14 +541,14 @@ class FeatureVolumeManager(CostVolumeManager):
                 lin[1].bias, lin[2].weight, lin[2].bias)
             return cost, (lowest if want_lowest else None), planes_ret, (mask if return_mask else None)
         return self._run_fused(cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK, min_depth,
-                               max_depth, depth_planes_bdhw, return_mask, want_lowest)
+                               max_depth, depth_planes_bdhw, return_mask, want_lowest, raw_poses=raw_poses)
 
     def _run_fused(self, cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK, min_depth,
-                   max_depth, depth_planes_bdhw, return_mask, want_lowest, allow_grad=False):
+                   max_depth, depth_planes_bdhw, return_mask, want_lowest, allow_grad=False, raw_poses=None):
         lib = _native.load()
         dev, shape, t, cams, pl, planes_ret, keep = self._prepare(
             cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK, min_depth,
-            max_depth, depth_planes_bdhw, need_poses=True, allow_grad=allow_grad)
+            max_depth, depth_planes_bdhw, need_poses=True, allow_grad=allow_grad, raw_poses=raw_poses)
         n_features = shape.C * (shape.K + 1) + 10 * shape.K + 4
         w, wkeep = self._mlp_weights(dev, n_features)
         wkeep.append(self._attach_packed_image(dev, shape, w, wkeep))

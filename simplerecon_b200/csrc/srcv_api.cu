@@ -51,6 +51,10 @@ static int32_t check_shape(const srcv_shape* s) {
   if ((long long)s->H * s->W > (1ll << 26) || s->K > 64 || s->C > 1024 ||
       (long long)s->B * s->D * s->H * s->W > (1ll << 40))
     return fail(SRCV_ERR_SHAPE, "dimension out of supported range");
+  if (s->layout != SRCV_LAYOUT_NCHW && s->layout != SRCV_LAYOUT_CHUNK_PLANAR)
+    return fail(SRCV_ERR_UNSUPPORTED, "unknown feature layout %d", s->layout);
+  if (s->layout == SRCV_LAYOUT_CHUNK_PLANAR && (s->C % 4) != 0)
+    return fail(SRCV_ERR_SHAPE, "chunk-planar features need C %% 4 == 0");
   return SRCV_OK;
 }
 
@@ -61,9 +65,14 @@ static int32_t check_common(const srcv_shape* s, const float* cur, const float* 
   if (!cur || !src || !cost) return fail(SRCV_ERR_NULL, "cur_feats/src_feats/cost is NULL");
   if (((reinterpret_cast<uintptr_t>(cur) | reinterpret_cast<uintptr_t>(src)) & 15u) != 0)
     return fail(SRCV_ERR_UNSUPPORTED, "cur_feats / src_feats must be 16-byte aligned");
-  if (!cams || !cams->src_extrinsics || !cams->src_Ks || !cams->cur_invK)
-    return fail(SRCV_ERR_NULL, "camera block incomplete");
-  if (need_poses && !cams->src_poses) return fail(SRCV_ERR_NULL, "src_poses is NULL");
+  if (!cams || !cams->src_Ks || !cams->cur_invK) return fail(SRCV_ERR_NULL, "camera block incomplete");
+  if (!cams->src_extrinsics) {
+    // raw poses: the prep kernel forms the relative transforms itself
+    if (!cams->src_cam_T_world || !cams->cur_world_T_cam || !cams->cur_cam_T_world || !cams->src_world_T_cam)
+      return fail(SRCV_ERR_NULL, "src_extrinsics is NULL and the raw pose block is incomplete");
+  } else if (need_poses && !cams->src_poses) {
+    return fail(SRCV_ERR_NULL, "src_poses is NULL");
+  }
   if (!pl) return fail(SRCV_ERR_NULL, "planes descriptor is NULL");
   switch (pl->mode) {
     case SRCV_PLANES_FROM_RANGE:
@@ -151,11 +160,14 @@ int32_t srcv_dot_forward_f32(const srcv_shape* s, const float* cur, const float*
   const bool fast = use_fast_dot(*s);
   if (g_variant.load() == SRCV_VARIANT_FAST && !fast)
     return fail(SRCV_ERR_UNSUPPORTED, "fast dot variant needs C == 16 and K <= 8");
+  if (s->layout == SRCV_LAYOUT_CHUNK_PLANAR && !fast)
+    return fail(SRCV_ERR_UNSUPPORTED, "chunk-planar features are served by the chunk-planar dot sweep only (C == 16, variant != generic)");
   const Workspace need = carve_workspace(*s, nullptr, dot_fast_supported(*s), 0);
   if (int32_t e = check_workspace(workspace, workspace_bytes, need.bytes)) return e;
   Workspace ws = carve_workspace(*s, workspace, dot_fast_supported(*s), 0);
   if (!fast) { ws.src_c4 = nullptr; ws.tile_done = nullptr; }  // skip the chunk-planar copies
   ws.cur_c4 = nullptr;             // the dot kernel keeps the reference features in registers
+  if (s->layout == SRCV_LAYOUT_CHUNK_PLANAR) ws.src_c4 = const_cast<float*>(src);   // gathered in place, no copy
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ProfRecord* pr = prof_next();
   if (pr) cudaEventRecord(pr->e[0], stream);
@@ -193,6 +205,7 @@ int32_t srcv_dot_backward_f32(const srcv_shape* s, const float* cur, const float
   if (!grad_cur || !grad_src) return fail(SRCV_ERR_NULL, "grad_cur / grad_src is NULL");
   if (!dot_backward_supported(*s))
     return fail(SRCV_ERR_UNSUPPORTED, "dot backward is built for C in {8, 16, 32}, got %d", s->C);
+  if (s->layout != SRCV_LAYOUT_NCHW) return fail(SRCV_ERR_UNSUPPORTED, "the backward kernels take NCHW features");
   const Workspace need = carve_workspace(*s, nullptr, false, 0);
   if (int32_t e = check_workspace(workspace, workspace_bytes, need.bytes)) return e;
   Workspace ws = carve_workspace(*s, workspace, false, 0);
@@ -223,6 +236,7 @@ static int32_t warp_planes_impl(const srcv_shape* s, const float* src, const src
     return fail(SRCV_ERR_NULL, "warp_features pointer is NULL");
   if (!cams || !cams->src_extrinsics || !cams->src_Ks || !cams->cur_invK)
     return fail(SRCV_ERR_NULL, "camera block incomplete");
+  if (s->layout != SRCV_LAYOUT_NCHW) return fail(SRCV_ERR_UNSUPPORTED, "warp_features takes NCHW features");
   if (s->D > 65535) return fail(SRCV_ERR_SHAPE, "at most 65535 planes per warp call");
   const Workspace need = carve_workspace(*s, nullptr, false, 0);
   if (int32_t e = check_workspace(workspace, workspace_bytes, need.bytes)) return e;
@@ -313,6 +327,8 @@ int32_t srcv_mlp_forward_f32(const srcv_shape* s, const float* cur, const float*
   const bool tc = use_tc_mlp(*s, *w);
   if (g_variant.load() == SRCV_VARIANT_FAST && !tc)
     return fail(SRCV_ERR_UNSUPPORTED, "tensor-core MLP variant needs K == 7, C == 16, hidden widths 128/128");
+  if (s->layout == SRCV_LAYOUT_CHUNK_PLANAR && !tc)
+    return fail(SRCV_ERR_UNSUPPORTED, "chunk-planar features are served by the tensor-core MLP sweep only (K == 7, C == 16, 128/128, variant != generic)");
   const size_t extra = mlp_extra_bytes(*s, *w);
   const bool c4 = mlp_tc_supported(*s, *w);
   const Workspace need = carve_workspace(*s, nullptr, c4, extra);
@@ -320,6 +336,10 @@ int32_t srcv_mlp_forward_f32(const srcv_shape* s, const float* cur, const float*
   Workspace ws = carve_workspace(*s, workspace, c4, extra);
   if (!tc) ws.src_c4 = nullptr;  // skip the chunk-planar copy
   ws.tile_done = nullptr;        // only the dot sweep uses the tile counters
+  if (s->layout == SRCV_LAYOUT_CHUNK_PLANAR) {   // gathered in place, no copy
+    ws.src_c4 = const_cast<float*>(src);
+    ws.cur_c4 = const_cast<float*>(cur);
+  }
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ProfRecord* pr = prof_next();
   if (pr) cudaEventRecord(pr->e[0], stream);
@@ -366,6 +386,7 @@ int32_t srcv_mlp_backward_f32(const srcv_shape* s, const float* cur, const float
     return fail(SRCV_ERR_NULL, "a parameter-gradient pointer is NULL");
   if (!mlp_backward_supported(*s, *w))
     return fail(SRCV_ERR_UNSUPPORTED, "MLP backward supports at most 208 input features and hidden widths <= 128");
+  if (s->layout != SRCV_LAYOUT_NCHW) return fail(SRCV_ERR_UNSUPPORTED, "the backward kernels take NCHW features");
   const size_t extra = mlp_backward_extra_bytes(*s, *w);
   const Workspace need = carve_workspace(*s, nullptr, false, extra);
   if (int32_t e = check_workspace(workspace, workspace_bytes, need.bytes)) return e;
@@ -389,6 +410,21 @@ int32_t srcv_mlp_backward_f32(const srcv_shape* s, const float* cur, const float
   g_last_variant.store("mlp_backward_fp32_recompute");
   err = launch_mlp_backward(*s, cur, src, ws, planes, per_pixel, *w, grad_cost, grad_cur, grad_src, *g, stream);
   if (err != cudaSuccess) return cuda_fail(err, g_last_variant.load());
+  return SRCV_OK;
+}
+
+int32_t srcv_instnorm_to_chunk_planar_f32(const float* x, int32_t B, int32_t V, int32_t C, int32_t H, int32_t W,
+                                          float eps, float* cur_c4, float* src_c4, void* stream_) {
+  if (!x || !cur_c4 || (V > 1 && !src_c4)) return fail(SRCV_ERR_NULL, "instnorm pointer is NULL");
+  if (B <= 0 || V <= 0 || C <= 0 || H <= 0 || W <= 0 || (C % 4) != 0 || (long long)H * W > (1ll << 26) ||
+      (long long)B * V * (C / 4) > 2147483647ll)
+    return fail(SRCV_ERR_SHAPE, "bad shape B=%d V=%d C=%d H=%d W=%d (C must be a multiple of 4)", B, V, C, H, W);
+  if (!(eps >= 0.f)) return fail(SRCV_ERR_SHAPE, "eps must be non-negative");
+  if (((reinterpret_cast<uintptr_t>(cur_c4) | reinterpret_cast<uintptr_t>(src_c4)) & 15u) != 0)
+    return fail(SRCV_ERR_UNSUPPORTED, "chunk-planar outputs must be 16-byte aligned");
+  g_last_variant.store("instnorm_chunk_planar");
+  cudaError_t err = launch_instnorm_c4(x, B, V, C, H, W, eps, cur_c4, src_c4, static_cast<cudaStream_t>(stream_));
+  if (err != cudaSuccess) return cuda_fail(err, "instnorm_to_chunk_planar");
   return SRCV_OK;
 }
 

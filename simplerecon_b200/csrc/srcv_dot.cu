@@ -145,10 +145,16 @@ dot_fast_kernel(srcv_shape s, const float* __restrict__ cur, const float4* __res
   const float dx = ((float)ox + 0.5f) - ctr.half_w, dy = ((float)oy + 0.5f) - ctr.half_h;
 
   float4 cur4[kNChunk];
+  if (s.layout == SRCV_LAYOUT_CHUNK_PLANAR) {     // producer already wrote (B,C/4,H,W,4)
 #pragma unroll
-  for (int j = 0; j < kNChunk; ++j) {
-    const float* cp = cur + ((size_t)b * kFastC + 4 * j) * HW + p;
-    cur4[j] = make_float4(__ldg(cp), __ldg(cp + HW), __ldg(cp + 2 * (size_t)HW), __ldg(cp + 3 * (size_t)HW));
+    for (int j = 0; j < kNChunk; ++j)
+      cur4[j] = __ldg(reinterpret_cast<const float4*>(cur) + ((size_t)b * kNChunk + j) * HW + p);
+  } else {
+#pragma unroll
+    for (int j = 0; j < kNChunk; ++j) {
+      const float* cp = cur + ((size_t)b * kFastC + 4 * j) * HW + p;
+      cur4[j] = make_float4(__ldg(cp), __ldg(cp + HW), __ldg(cp + 2 * (size_t)HW), __ldg(cp + 3 * (size_t)HW));
+    }
   }
   float best = 0.f, best_d = 0.f;
 

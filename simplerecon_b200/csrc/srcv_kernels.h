@@ -51,6 +51,7 @@ cudaError_t launch_dot_generic(const srcv_shape& s, const float* cur, const floa
                                float* cost, float* lowest, cudaStream_t stream);
 bool dot_fast_supported(const srcv_shape& s);
 size_t dot_fast_tile_counters(const srcv_shape& s);
+// `cur` is NCHW, or chunk-planar (B,C/4,H,W,4) when s.layout says so
 cudaError_t launch_dot_fast(const srcv_shape& s, const float* cur, const Workspace& ws,
                             const float* planes, bool per_pixel, float* cost, float* lowest,
                             cudaStream_t stream);
@@ -92,6 +93,10 @@ cudaError_t launch_mlp_tc(const srcv_shape& s, const float* cur, const Workspace
                           float* lowest, uint8_t* mask, cudaStream_t stream);
 cudaError_t launch_tc_selftest(const float* A, const float* Wm, int Kp, float* Dout, void* scratch,
                                cudaStream_t stream);
+
+// producer-side fusion (csrc/srcv_producer.cu): InstanceNorm2d + chunk-planar layout
+cudaError_t launch_instnorm_c4(const float* x, int B, int V, int C, int H, int W, float eps, float* cur_c4,
+                               float* src_c4, cudaStream_t stream);
 
 // dense-grid TSDF integration (csrc/srcv_tsdf.cu)
 size_t tsdf_workspace_bytes(int frames);

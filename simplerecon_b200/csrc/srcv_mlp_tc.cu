@@ -74,11 +74,17 @@ constexpr float kUnscale2 = 1.0f / (kWScale * kWScale);
 // post-processes accumulator columns [32q, 32q+32).  Warp 16 issues the MMAs; warps 17-19
 // complete its warpgroup (setmaxnreg works on aligned groups of four warps): the kernel is
 // launched at 96 registers per thread, the MMA group shrinks to 24 and the 16 worker warps
-// grow to 120 — room for all 16 vector loads of a bilinear footprint in flight.
+// grow to 112 — room for all 16 vector loads of a bilinear footprint in flight.
+// setmaxnreg only REDISTRIBUTES the CTA's launch-time allocation (640 x 96 registers): an .inc
+// blocks until the pool holds enough, so the totals below must fit it or the CTA deadlocks.
 constexpr int kWorkWarps = 16, kMmaWarp = 16;
 constexpr int kThreads = 20 * 32;
 constexpr int kWorkers = kWorkWarps * 32;
-constexpr int kRegsWorker = 120, kRegsMma = 24;
+constexpr int kRegsLaunch = 96;          // what ptxas allocates under __launch_bounds__(640, 1)
+constexpr int kRegsWorker = 112, kRegsMma = 24;
+static_assert(kWorkers * kRegsWorker + (kThreads - kWorkers) * kRegsMma <= kThreads * kRegsLaunch,
+              "setmaxnreg budget: increases must be covered by the decreases within the CTA's launch allocation");
+static_assert(kRegsWorker % 8 == 0 && kRegsMma % 8 == 0, "setmaxnreg takes multiples of 8");
 
 // shared memory image (bytes)
 constexpr uint32_t kW1Bytes = kN * kK1 * 2, kW2Bytes = kN * kK2 * 2;   // one of (hi, lo)

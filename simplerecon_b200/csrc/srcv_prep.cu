@@ -79,8 +79,20 @@ __device__ void view_params(const float* __restrict__ Kmat, const float* __restr
   }
 }
 
+__device__ void mat4_product(const float* __restrict__ A, const float* __restrict__ B, float* out) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      double a = 0.0;
+#pragma unroll
+      for (int l = 0; l < 4; ++l) a += (double)A[r * 4 + l] * (double)B[l * 4 + c];
+      out[r * 4 + c] = (float)a;
+    }
+}
+
 __global__ void __launch_bounds__(256)
-prep_kernel(srcv_shape s, srcv_cameras cams, srcv_planes pl, const float* __restrict__ src,
+prep_kernel(srcv_shape s, srcv_cameras cams, srcv_planes pl, bool need_pose_block, const float* __restrict__ src,
             const float* __restrict__ cur, float* __restrict__ planes_ws,
             ViewParams* __restrict__ views, FrameParams* __restrict__ frames,
             float* __restrict__ src_c4, float* __restrict__ cur_c4,
@@ -124,8 +136,17 @@ prep_kernel(srcv_shape s, srcv_cameras cams, srcv_planes pl, const float* __rest
   i -= n_done;
   if (i < nv) {
     const long long b = i / s.K;
-    view_params(cams.src_Ks + i * 16, cams.src_extrinsics + i * 16, cams.cur_invK + b * 16,
-                cams.src_poses ? cams.src_poses + i * 16 : nullptr, s.W, s.H, views + i);
+    if (cams.src_extrinsics == nullptr) {
+      // raw poses: the two batched 4x4 products of experiment_modules/depth_model.py:324-332,
+      // fp64 accumulation, one rounding to fp32 (what the fp32 matmul yields up to its last bit)
+      float E[16], P[16];
+      mat4_product(cams.src_cam_T_world + i * 16, cams.cur_world_T_cam + b * 16, E);
+      mat4_product(cams.cur_cam_T_world + b * 16, cams.src_world_T_cam + i * 16, P);
+      view_params(cams.src_Ks + i * 16, E, cams.cur_invK + b * 16, need_pose_block ? P : nullptr, s.W, s.H, views + i);
+    } else {
+      view_params(cams.src_Ks + i * 16, cams.src_extrinsics + i * 16, cams.cur_invK + b * 16,
+                  cams.src_poses ? cams.src_poses + i * 16 : nullptr, s.W, s.H, views + i);
+    }
     return;
   }
   i -= nv;
@@ -202,17 +223,19 @@ cudaError_t launch_prep(const srcv_shape& s, const srcv_cameras& cams, const src
                         bool need_poses, cudaStream_t stream) {
   srcv_cameras c = cams;
   if (!need_poses) c.src_poses = nullptr;
+  // chunk-planar inputs are gathered in place: no re-layout copy (the sweeps read the caller's buffers)
+  const bool copy_c4 = s.layout != SRCV_LAYOUT_CHUNK_PLANAR;
   const long long nv = (long long)s.B * s.K;
   const long long np = (pl.mode == SRCV_PLANES_FROM_RANGE) ? (long long)s.B * s.D : 0;
-  const long long nt = ws.src_c4 ? nv * (s.C / 4) * s.H * s.W : 0;
-  const long long ncur = (ws.src_c4 && ws.cur_c4) ? (long long)s.B * (s.C / 4) * s.H * s.W : 0;
+  const long long nt = (ws.src_c4 && copy_c4) ? nv * (s.C / 4) * s.H * s.W : 0;
+  const long long ncur = (ws.src_c4 && ws.cur_c4 && copy_c4) ? (long long)s.B * (s.C / 4) * s.H * s.W : 0;
   const long long ppt = (((long long)s.H * s.W) & 3) == 0 ? 4 : 1;
   const long long ndone = ws.tile_done ? (long long)ws.tile_done_count : 0;
   const long long total = nt / ppt + ncur / ppt + ndone + nv + s.B + np;
   const int threads = 256;
   const long long blocks = (total + threads - 1) / threads;
-  SRCV_LAUNCH(prep_kernel, (unsigned)blocks, threads, 0, stream, s, c, pl, src_feats, cur_feats, ws.planes,
-              ws.views, ws.frames, ws.src_c4, ncur ? ws.cur_c4 : nullptr, ws.tile_done, ndone);
+  SRCV_LAUNCH(prep_kernel, (unsigned)blocks, threads, 0, stream, s, c, pl, need_poses, src_feats, cur_feats, ws.planes,
+              ws.views, ws.frames, nt ? ws.src_c4 : nullptr, ncur ? ws.cur_c4 : nullptr, ws.tile_done, ndone);
   note_launch();
   return cudaGetLastError();
 }

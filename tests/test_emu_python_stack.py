@@ -266,3 +266,42 @@ def test_fast_manager_warp_features_five_tuple(emulated):
         assert torch.allclose(world, rw, rtol=1e-6, atol=1e-7) and torch.equal(mask, rm)
         assert torch.allclose(depths, rd, rtol=2e-6, atol=1e-6) and torch.allclose(pix, rp, rtol=0, atol=2e-4)
         assert (warped - rf).abs().max().item() <= 4e-5 * rf.abs().max().item() + 1e-6
+
+
+def test_producer_side_fusion_chunk_planar_and_raw_poses(emulated):
+    """(1) instance_norm_to_chunk_planar == nn.InstanceNorm2d(16) (reference
+    modules/networks.py:201) written in the gather layout; (2) both sweeps on chunk-planar inputs
+    equal the NCHW path bit for bit (same values, no prep copy); (3) raw poses: the prep kernel's
+    relative transforms (depth_model.py:324-332) reproduce the call with PyTorch-side products."""
+    B, K, C, H, W, D = 2, 7, 16, 10, 16, 4
+    t = make_tuple(B, K, H, W, channels=C, seed=41)
+    g = torch.Generator().manual_seed(42)
+    x = 3.0 * torch.randn(B, 1 + K, C, H, W, generator=g) + 0.7
+    cur_c4, src_c4 = S.instance_norm_to_chunk_planar(x)
+    ref = torch.nn.InstanceNorm2d(C)(x.reshape(B * (1 + K), C, H, W)).reshape(B, 1 + K, C, H, W)
+    back = lambda c4: c4.movedim(-1, -3).flatten(-4, -3)        # (..., C/4, H, W, 4) -> (..., C, H, W)
+    assert cur_c4.shape == (B, C // 4, H, W, 4) and src_c4.shape == (B, K, C // 4, H, W, 4)
+    assert (back(cur_c4) - ref[:, 0]).abs().max().item() < 3e-6
+    assert (back(src_c4) - ref[:, 1:]).abs().max().item() < 3e-6
+    nchw = dict(t, cur_feats=back(cur_c4).contiguous(), src_feats=back(src_c4).contiguous())
+    c4 = dict(t, cur_feats=cur_c4, src_feats=src_c4)
+    # world poses whose products are the tuple's relative transforms
+    world_T_cur = torch.linalg.inv(make_tuple(B, 1, H, W, seed=43)["src_extrinsics"][:, 0].double())
+    cur_T_world = torch.linalg.inv(world_T_cur)
+    raw = dict(src_cam_T_world=(t["src_extrinsics"].double() @ cur_T_world[:, None]).float(),
+               src_world_T_cam=(world_T_cur[:, None] @ t["src_poses"].double()).float(),
+               cur_cam_T_world=cur_T_world.float(), cur_world_T_cam=world_T_cur.float())
+    for m in (S.CostVolumeManager(H, W, num_depth_bins=D), _hero(K, C, H, W, D)):
+        with torch.no_grad():
+            a = m(**nchw, return_mask=True)
+            b = m(**c4, return_mask=True)
+            r = m(**{**nchw, "src_extrinsics": None, "src_poses": None}, return_mask=True, raw_poses=raw)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+        if a[3] is not None:
+            assert torch.equal(a[3], b[3])
+        tol = 2e-4 * float(a[0].abs().max())      # the raw poses went through an fp32 round trip
+        assert (r[0] - a[0]).abs().max().item() <= tol
+    # gradients are refused on the chunk-planar path (the backward kernels take NCHW)
+    c4g = dict(c4, cur_feats=cur_c4.clone().requires_grad_(True))
+    with pytest.raises(NotImplementedError):
+        S.CostVolumeManager(H, W, num_depth_bins=D)(**c4g)
