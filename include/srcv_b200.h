@@ -293,6 +293,30 @@ size_t srcv_tsdf_workspace_bytes(const srcv_tsdf_frames* frames);
 int32_t srcv_tsdf_integrate_f16(const srcv_tsdf_volume* volume, const srcv_tsdf_frames* frames,
                                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- multi-view depth consistency (point-cloud fusion) ------------------------------ *
+ * Replaces process_depth of the reference's 3DVNet-style fuser (tools/torch_point_cloud_fusion.py
+ * :12-97), which pc_fusion.py:158 runs for every frame of a scan against all the others: for each
+ * pixel of frame `ref_index`, un-project, re-project into every other frame, nearest-sample its
+ * depth, count the frames that agree within z_thresh, and average the back-projected consistent
+ * samples with the pixel's own point.  fp32, the reference's operation order.
+ *   scan: N frames — depths (N,H,W), K and K_inv (N,3,3), cam_T_world and world_T_cam (N,4,4)
+ *         (the caller inverts once per scan; the reference inverts per call, :25-27), all DEVICE
+ *   pts_avg (H*W,3) out    n_valid (H*W) int32 out    valid (H*W) uint8 out (n_valid >= n_consistent)
+ * The workspace keeps the staged per-frame matrices: pass frames_ready != 0 on every call after
+ * the first of a scan to skip re-staging them.                                              */
+typedef struct srcv_mvs_scan {
+  const float* depths;
+  const float* K;
+  const float* K_inv;
+  const float* cam_T_world;
+  const float* world_T_cam;
+  int32_t N, H, W;
+} srcv_mvs_scan;
+size_t srcv_mvs_workspace_bytes(const srcv_mvs_scan* scan);
+int32_t srcv_mvs_consistency_f32(const srcv_mvs_scan* scan, int32_t ref_index, float z_thresh,
+                                 int32_t n_consistent, float* pts_avg, int32_t* n_valid, uint8_t* valid,
+                                 void* workspace, size_t workspace_bytes, int32_t frames_ready, void* stream);
+
 /* ---- tuning / introspection ------------------------------------------- *
  * Selects the kernel variant used by the two forward calls on this thread's
  * next invocations (process-global).  0 = automatic choice.  Used by the tests

@@ -66,6 +66,11 @@ class TsdfFrames(C.Structure):
                 ("H", C.c_int32), ("W", C.c_int32), ("min_depth", C.c_float), ("max_depth", C.c_float)]
 
 
+class MvsScan(C.Structure):
+    _fields_ = [("depths", _fp), ("K", _fp), ("K_inv", _fp), ("cam_T_world", _fp), ("world_T_cam", _fp),
+                ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32)]
+
+
 # every symbol include/srcv_b200.h declares: (restype, argtypes)
 SYMBOLS = {
     "srcv_abi_version": (C.c_int32, []),
@@ -99,6 +104,9 @@ SYMBOLS = {
                                                       C.c_float, _fp, _fp, _fp]),
     "srcv_tsdf_workspace_bytes": (C.c_size_t, [C.POINTER(TsdfFrames)]),
     "srcv_tsdf_integrate_f16": (C.c_int32, [C.POINTER(TsdfVolume), C.POINTER(TsdfFrames), _fp, C.c_size_t, _fp]),
+    "srcv_mvs_workspace_bytes": (C.c_size_t, [C.POINTER(MvsScan)]),
+    "srcv_mvs_consistency_f32": (C.c_int32, [C.POINTER(MvsScan), C.c_int32, C.c_float, C.c_int32, _fp, _fp, _fp,
+                                             _fp, C.c_size_t, C.c_int32, _fp]),
     "srcv_set_variant": (C.c_int32, [C.c_int32]),
     "srcv_last_variant": (C.c_char_p, []),
     "srcv_launch_count": (C.c_uint64, []),

@@ -289,7 +289,7 @@ static bool use_tc_mlp(const srcv_shape& s, const srcv_mlp_weights& w) {
 
 static size_t mlp_extra_bytes(const srcv_shape& s, const srcv_mlp_weights& w) {
   size_t e = mlp_generic_extra_bytes(s, w);
-  if (mlp_tc_supported(s, w) && mlp_tc_extra_bytes() > e) e = mlp_tc_extra_bytes();
+  if (mlp_tc_supported(s, w) && mlp_tc_extra_bytes(s) > e) e = mlp_tc_extra_bytes(s);
   return e;
 }
 
@@ -452,6 +452,30 @@ int32_t srcv_tsdf_integrate_f16(const srcv_tsdf_volume* v, const srcv_tsdf_frame
   g_last_variant.store("tsdf_integrate_f16");
   cudaError_t err = launch_tsdf_integrate(*v, *f, workspace, static_cast<cudaStream_t>(stream_));
   if (err != cudaSuccess) return cuda_fail(err, "tsdf_integrate");
+  return SRCV_OK;
+}
+
+size_t srcv_mvs_workspace_bytes(const srcv_mvs_scan* s) {
+  if (!s || s->N <= 0) return 0;
+  return mvs_workspace_bytes(s->N);
+}
+
+int32_t srcv_mvs_consistency_f32(const srcv_mvs_scan* s, int32_t ref, float z_thresh, int32_t n_consistent,
+                                 float* pts_avg, int32_t* n_valid, uint8_t* valid, void* workspace,
+                                 size_t workspace_bytes, int32_t frames_ready, void* stream_) {
+  if (!s) return fail(SRCV_ERR_NULL, "scan descriptor is NULL");
+  if (!s->depths || !s->K || !s->K_inv || !s->cam_T_world || !s->world_T_cam)
+    return fail(SRCV_ERR_NULL, "a scan pointer is NULL");
+  if (!pts_avg || !n_valid || !valid) return fail(SRCV_ERR_NULL, "an output pointer is NULL");
+  if (s->N <= 0 || s->H <= 1 || s->W <= 1 || (long long)s->H * s->W > (1ll << 26) ||
+      (long long)s->N * s->H * s->W > (1ll << 40))
+    return fail(SRCV_ERR_SHAPE, "bad scan shape N=%d H=%d W=%d", s->N, s->H, s->W);
+  if (ref < 0 || ref >= s->N) return fail(SRCV_ERR_SHAPE, "ref_index %d out of range [0,%d)", ref, s->N);
+  if (int32_t e = check_workspace(workspace, workspace_bytes, mvs_workspace_bytes(s->N))) return e;
+  g_last_variant.store("mvs_consistency_f32");
+  cudaError_t err = launch_mvs_consistency(*s, ref, z_thresh, n_consistent, pts_avg, n_valid, valid, workspace,
+                                           frames_ready != 0, static_cast<cudaStream_t>(stream_));
+  if (err != cudaSuccess) return cuda_fail(err, "mvs_consistency");
   return SRCV_OK;
 }
 

@@ -85,7 +85,7 @@ cudaError_t launch_mlp_backward(const srcv_shape& s, const float* cur, const flo
 
 // tensor-core variant (tcgen05): K = 7, C = 16, 202 -> 128 -> 128 -> 1
 bool mlp_tc_supported(const srcv_shape& s, const srcv_mlp_weights& w);
-size_t mlp_tc_extra_bytes();
+size_t mlp_tc_extra_bytes(const srcv_shape& s);
 size_t mlp_tc_image_bytes();
 cudaError_t launch_mlp_tc_pack(const srcv_mlp_weights& w, void* image, cudaStream_t stream);
 cudaError_t launch_mlp_tc(const srcv_shape& s, const float* cur, const Workspace& ws,
@@ -102,6 +102,12 @@ cudaError_t launch_instnorm_c4(const float* x, int B, int V, int C, int H, int W
 size_t tsdf_workspace_bytes(int frames);
 cudaError_t launch_tsdf_integrate(const srcv_tsdf_volume& v, const srcv_tsdf_frames& f, void* workspace,
                                   cudaStream_t stream);
+
+// multi-view depth consistency (csrc/srcv_mvs.cu)
+size_t mvs_workspace_bytes(int n);
+cudaError_t launch_mvs_consistency(const srcv_mvs_scan& s, int ref, float z_thresh, int n_consistent,
+                                   float* pts_avg, int* n_valid, uint8_t* valid, void* workspace,
+                                   bool frames_ready, cudaStream_t stream);
 
 // argmax over planes -> plane depth (used by variants that do not fuse it)
 cudaError_t launch_argmax(const srcv_shape& s, const float* cost, const float* planes,

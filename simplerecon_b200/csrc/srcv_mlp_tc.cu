@@ -5,35 +5,33 @@
 // K = 7 source views, C = 16 channels, MLP 202 -> 128 -> 128 -> 1.
 //
 // One persistent CTA per SM walks over row tiles; a tile = 128 rows = a 16 x 2 patch of
-// pixels at four consecutive depth planes.  Sixteen "row worker" warps (four threads per row) and one
-// MMA-issuing thread run this per-tile pipeline:
-//   1. the workers project, gather (chunk-planar copies of the features, csrc/srcv_prep.cu)
-//      and build the row's 202 metadata channels in registers, split every value into an
-//      fp16 (hi, lo) pair and write them straight into TENSOR MEMORY as the A operand
-//      (tcgen05.st) — the (B,F,H,W) / (B*D,H,W,F) tensors the reference materialises exist
-//      only as 208 TMEM columns per row;
-//   2. layer 1 = 13 x 3 tcgen05.mma (A from TMEM, weights from shared memory, fp32
-//      accumulator in TMEM):  A_hi W_hi + A_hi W_lo + A_lo W_hi.  The bias rides in the MMA
-//      (a constant-one K position against a 16 b1 weight row);
-//   3. the workers read the accumulator (each its 32 columns), apply LeakyReLU, split to
-//      fp16 (hi, lo) and write the layer-2 A operand back IN PLACE — a thread's 32 fp32
-//      accumulator columns become its 16 hi + 16 lo operand columns, so no other thread's
-//      columns are touched and no cross-thread ordering is needed;
-//   4. layer 2 = 8 x 3 tcgen05.mma into a SECOND accumulator region;
-//   5. the workers apply bias + LeakyReLU and the 128 -> 1 layer as partial dots, reduced in
-//      a fixed order through shared memory, and store the cost.
-// Stages are chained by mbarriers (tcgen05.commit for MMA completion).  Because layer 2
-// accumulates into its own TMEM columns, the layer-1 MMAs of tile t+1 run while the workers
-// are still in step 5 of tile t; a worker builds the first K block of tile t+1 while tile
-// t's layer-1 MMAs run and the second one while its layer-2 MMAs run.  The tensor pipe only
-// idles during step 3.
+// pixels at four consecutive depth planes.  Warp roles (640 threads):
+//   * 12 BUILDER warps, three threads per row: project, gather (chunk-planar copies of the
+//     features, csrc/srcv_prep.cu) and build the row's 202 metadata channels in registers, split
+//     every value into an fp16 (hi, lo) pair and write them straight into TENSOR MEMORY as the
+//     A operand (tcgen05.st) — the (B,F,H,W) / (B*D,H,W,F) tensors the reference materialises
+//     exist only as 208 TMEM columns per row;
+//   * 1 MMA-issuing thread: layer 1 = 13 x 3 tcgen05.mma (A from TMEM, weights from shared
+//     memory, fp32 accumulator in TMEM):  A_hi W_hi + A_hi W_lo + A_lo W_hi — the bias rides in
+//     the MMA (a constant-one K position against a 16 b1 weight row); layer 2 = 8 x 3
+//     tcgen05.mma into a SECOND accumulator region;
+//   * 4 EPILOGUE warps, one thread per row: after layer 1 they read the accumulator 32 columns
+//     at a time, apply LeakyReLU, split to fp16 (hi, lo) and write the layer-2 A operand back IN
+//     PLACE (a chunk's 32 fp32 columns become its 16 hi + 16 lo operand columns, so nothing else
+//     is touched); after layer 2 they apply bias + LeakyReLU and the 128 -> 1 layer as one dot
+//     product per row and store the cost.
+// Stages are chained by mbarriers (tcgen05.commit for MMA completion).  The roles overlap: the
+// builders gather tile t+1 (L1-bound) while the epilogue warps post-process tile t (ALU-bound)
+// and the tensor pipe runs its MMAs; because layer 2 accumulates into its own TMEM columns, the
+// layer-1 MMAs of tile t+1 start while the layer-2 epilogue of tile t is still running.  The
+// tensor pipe only idles during the layer-1 epilogue.
 // Weights (both layers, hi and lo, 168 KB) stay resident in shared memory for the
 // CTA's lifetime, laid out as K-major no-swizzle core matrices by the pack kernel.
 //
 // The K order of layer 1 is OURS (the pack kernel permutes W1's columns to match):
 //   per view k (26 channels): 16 warped | mask | z' | dot | ray angle | n_src (3) | comb | r | t
 //   tail (21 + 5 pad):        16 reference features | plane depth | n_cur (3) | ONE (bias) | zeros
-// i.e. every worker thread writes 2 x 26 = 52 consecutive K positions.
+// i.e. a builder thread writes the 3 x 26 (or 2 x 26) consecutive K positions of its blocks.
 //
 // Scaling: W1 and W2 are stored x16 (exact) so the lo halves of typical |w| ~ 0.05 weights
 // stay out of the fp16 subnormals.  Layer 1 therefore yields 16 (W1 x + b1); LeakyReLU
@@ -55,36 +53,38 @@ constexpr int kRows = 128;               // rows (TMEM lanes) per tile
 // gathers for one source view walk along the same epipolar lines and share L1 lines.
 constexpr int kTileW = 16, kTileH = 2, kTileD = 4;
 constexpr int kN = 128;                  // layer widths
-constexpr int kBlk = kC + 10;            // channels per view block (26)
-constexpr int kK1 = 208;                 // 7*26 + 21 + 5 pad  (13 k-steps of 16)
+constexpr int kBlk = 24;                 // K positions per block (23 per view + 1 pad; tail 21 + 3 pad)
+constexpr int kBlkCols = kBlk / 2;       // 12 packed columns per block and half
+constexpr int kK1 = 192;                 // 8 blocks x 24  (12 k-steps of 16)
 constexpr int kK2 = 128;
 constexpr int kF = kC * (kViews + 1) + 10 * kViews + 4;  // 202
 constexpr int kBiasPos = kViews * kBlk + kC + 4;         // K position of the constant one
 
-// TMEM columns (32-bit): two K elements per column
-//   A1 hi | A1 lo | DA (layer-1 accumulator, then the layer-2 operand in place) | D2
-constexpr uint32_t kColA1Hi = 0, kColA1Lo = kK1 / 2, kColDA = kK1, kColD2 = kK1 + kN, kTmemCols = 512;
-static_assert(kColD2 + kN <= kTmemCols, "TMEM budget");
+// TMEM columns (32-bit): two K elements per column.  TWO A1 buffers (tile t uses buffer t & 1), so
+// the builders run a whole tile ahead of the tensor pipe; the layer-2 accumulator D2 of tile t
+// lands in the first 128 columns of tile t's own A1 buffer, which is dead once its layer-1 MMAs
+// are done.   A1[0]: hi 0..95 | lo 96..191    A1[1]: 192..383    DA: 384..511
+constexpr uint32_t kColA1 = 0, kA1Stride = kK1, kA1LoOff = kK1 / 2, kColDA = 2 * kK1, kTmemCols = 512;
+static_assert(kColDA + kN <= kTmemCols, "TMEM budget");
+static_assert(kN <= kK1, "D2 must fit in an A1 buffer");
 
 constexpr float kWScale = 16.0f;
 constexpr float kUnscale2 = 1.0f / (kWScale * kWScale);
 
-// 16 "row worker" warps: four threads per row (quarter q = warp / 4).  Every worker is
-// producer AND epilogue of its rows — it builds K blocks {2q, 2q+1} of the A operand and
-// post-processes accumulator columns [32q, 32q+32).  Warp 16 issues the MMAs; warps 17-19
-// complete its warpgroup (setmaxnreg works on aligned groups of four warps): the kernel is
-// launched at 96 registers per thread, the MMA group shrinks to 24 and the 16 worker warps
-// grow to 112 — room for all 16 vector loads of a bilinear footprint in flight.
+// Warps 0-11 build, 12-15 run the epilogues, 16 issues the MMAs; 17-19 complete its warpgroup
+// (setmaxnreg works on aligned groups of four warps): the kernel is launched at 96 registers per
+// thread, the MMA group shrinks to 24, builders grow to 112 (all 16 vector loads of a bilinear
+// footprint in flight) and the epilogue group to 120.
 // setmaxnreg only REDISTRIBUTES the CTA's launch-time allocation (640 x 96 registers): an .inc
 // blocks until the pool holds enough, so the totals below must fit it or the CTA deadlocks.
-constexpr int kWorkWarps = 16, kMmaWarp = 16;
+constexpr int kBuildWarps = 12, kEpiWarps = 4, kMmaWarp = 16;
 constexpr int kThreads = 20 * 32;
-constexpr int kWorkers = kWorkWarps * 32;
+constexpr int kBuilders = kBuildWarps * 32, kEpis = kEpiWarps * 32;
 constexpr int kRegsLaunch = 96;          // what ptxas allocates under __launch_bounds__(640, 1)
-constexpr int kRegsWorker = 112, kRegsMma = 24;
-static_assert(kWorkers * kRegsWorker + (kThreads - kWorkers) * kRegsMma <= kThreads * kRegsLaunch,
+constexpr int kRegsBuild = 112, kRegsEpi = 120, kRegsMma = 24;
+static_assert(kBuilders * kRegsBuild + kEpis * kRegsEpi + (kThreads - kBuilders - kEpis) * kRegsMma <= kThreads * kRegsLaunch,
               "setmaxnreg budget: increases must be covered by the decreases within the CTA's launch allocation");
-static_assert(kRegsWorker % 8 == 0 && kRegsMma % 8 == 0, "setmaxnreg takes multiples of 8");
+static_assert(kRegsBuild % 8 == 0 && kRegsEpi % 8 == 0 && kRegsMma % 8 == 0, "setmaxnreg takes multiples of 8");
 
 // shared memory image (bytes)
 constexpr uint32_t kW1Bytes = kN * kK1 * 2, kW2Bytes = kN * kK2 * 2;   // one of (hi, lo)
@@ -93,8 +93,7 @@ constexpr uint32_t kOffW1Hi = 0, kOffW1Lo = kW1Bytes, kOffW2Hi = 2 * kW1Bytes,
 constexpr uint32_t kVecFloats = 3 * kN + 4;   // b2 | 0.505 w3 | 0.495 w3 | b3
 constexpr uint32_t kOffBar = kOffVec + kVecFloats * 4;
 constexpr uint32_t kOffFlag = kOffBar + 8 * 8;            // 8 mbarrier slots
-constexpr uint32_t kOffPart = kOffFlag + 2 * 4 * kRows;   // mask bits [parity][quarter][row]
-constexpr uint32_t kSmemBytes = kOffPart + 2 * 4 * kRows * 4;  // layer-3 partial dots [parity][quarter][row]
+constexpr uint32_t kSmemBytes = kOffFlag + 2 * 3 * kRows;   // mask bits [parity][builder slot][row]
 // image = [W1hi | W1lo | W2hi | W2lo | vec] exactly as it sits in shared memory
 constexpr uint32_t kImageBytes = kOffBar;
 
@@ -104,7 +103,9 @@ __host__ __device__ inline uint32_t core_offset(int n, int k, int N) {
 }
 
 // reference channel index (modules/cost_volume.py:698-723 order) of OUR layer-1 K position;
-// -2 = the bias position (constant one in A), -1 = padding
+// -2 = the bias position (constant one in A), -1 = padding.  The 21 pose measures (comb, r, t per
+// view) are NOT in K: they are constant per (frame, view), so their layer-1 contribution is a
+// per-frame bias vector (tc_frame_bias_kernel) added in the layer-1 epilogue.
 __host__ __device__ inline int ref_channel(int kk) {
   if (kk < kViews * kBlk) {
     const int k = kk / kBlk, j = kk - k * kBlk;
@@ -116,9 +117,7 @@ __host__ __device__ inline int ref_channel(int kk) {
       case 2: return base + 2 * kViews + 1 + k;          // dot
       case 3: return base + 3 * kViews + 1 + k;          // ray angle
       case 4: case 5: case 6: return base + 4 * kViews + 4 + 3 * k + (j - kC - 4);  // n_src
-      case 7: return base + 7 * kViews + 4 + k;          // comb
-      case 8: return base + 8 * kViews + 4 + k;          // r
-      default: return base + 9 * kViews + 4 + k;         // t
+      default: return -1;                                // pad
     }
   }
   const int j = kk - kViews * kBlk;
@@ -127,6 +126,10 @@ __host__ __device__ inline int ref_channel(int kk) {
   if (j < kC + 4) return kC * (kViews + 1) + 4 * kViews + 1 + (j - kC - 1);  // n_cur
   if (kk == kBiasPos) return -2;                         // bias
   return -1;                                             // pad
+}
+// reference channels of the pose measures of view k: comb, r, t (:718-720)
+__host__ __device__ inline int pose_channel(int which, int k) {
+  return kC * (kViews + 1) + (7 + which) * kViews + 4 + k;
 }
 
 // Builds the shared-memory image from nn.Linear weights: fp16 (hi, lo) core matrices.
@@ -166,15 +169,28 @@ tc_pack_kernel(srcv_mlp_weights w, uint8_t* __restrict__ image) {
   }
 }
 
-// 13 packed columns of one K block -> TMEM (hi and lo regions)
-__device__ __forceinline__ void store_block(uint32_t tbase_lane, uint32_t col, const uint32_t (&hi)[13],
-                                            const uint32_t (&lo)[13]) {
-  st_x8(tbase_lane + kColA1Hi + col, hi);
-  st_x4(tbase_lane + kColA1Hi + col + 8, hi + 8);
-  st_x1(tbase_lane + kColA1Hi + col + 12, hi[12]);
-  st_x8(tbase_lane + kColA1Lo + col, lo);
-  st_x4(tbase_lane + kColA1Lo + col + 8, lo + 8);
-  st_x1(tbase_lane + kColA1Lo + col + 12, lo[12]);
+// pb[b][n] = 16 * sum_k ( W1[n, comb_k] comb(b,k) + W1[n, r_k] r(b,k) + W1[n, t_k] t(b,k) ): the
+// layer-1 contribution of the 21 pose measures, fp64 accumulation, added by the layer-1 epilogue.
+__global__ void __launch_bounds__(kN)
+tc_frame_bias_kernel(srcv_mlp_weights w, const ViewParams* __restrict__ views, float* __restrict__ pb) {
+  const int b = blockIdx.x, n = threadIdx.x;
+  double acc = 0.0;
+  for (int k = 0; k < kViews; ++k) {
+    const ViewParams& vp = views[b * kViews + k];
+    acc += (double)w.w1[(size_t)n * kF + pose_channel(0, k)] * (double)vp.comb;
+    acc += (double)w.w1[(size_t)n * kF + pose_channel(1, k)] * (double)vp.rmeas;
+    acc += (double)w.w1[(size_t)n * kF + pose_channel(2, k)] * (double)vp.tmeas;
+  }
+  pb[(size_t)b * kN + n] = (float)((double)kWScale * acc);
+}
+
+// 12 packed columns of one K block -> TMEM (hi and lo regions of the tile's A1 buffer)
+__device__ __forceinline__ void store_block(uint32_t a1_lane, uint32_t col, const uint32_t (&hi)[kBlkCols],
+                                            const uint32_t (&lo)[kBlkCols]) {
+  st_x8(a1_lane + col, hi);
+  st_x4(a1_lane + col + 8, hi + 8);
+  st_x8(a1_lane + kA1LoOff + col, lo);
+  st_x4(a1_lane + kA1LoOff + col + 8, lo + 8);
 }
 
 // What a worker thread keeps about the tile it builds the A operand for.
@@ -189,30 +205,28 @@ struct RowCtx {
   bool last_plane;           // the row's plane is D - 1 (the overall mask is taken there)
 };
 
-// The depth-invariant part of one (frame, view): five 16-byte loads (ViewParams is 128-byte
-// aligned; the struct order a0 hx hy t | centre comb | rmeas tmeas rt_hi rt_lo is what they read).
+// The depth-invariant part of one (frame, view): four 16-byte loads (ViewParams is 128-byte
+// aligned; the struct order a0 hx hy t | centre comb is what they read).
 struct ViewRegs {
-  float a0[3], hx[3], hy[3], t[3], centre[3], comb;
-  uint32_t rt_hi, rt_lo;     // (rmeas, tmeas) already split and packed by the prep kernel
+  float a0[3], hx[3], hy[3], t[3], centre[3];
 };
 __device__ __forceinline__ void load_view(const ViewParams* __restrict__ vp, ViewRegs& v) {
   const float4* p = reinterpret_cast<const float4*>(vp);
-  const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3), e = __ldg(p + 4);
+  const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
   v.a0[0] = a.x; v.a0[1] = a.y; v.a0[2] = a.z; v.hx[0] = a.w;
   v.hx[1] = b.x; v.hx[2] = b.y; v.hy[0] = b.z; v.hy[1] = b.w;
   v.hy[2] = c.x; v.t[0] = c.y; v.t[1] = c.z; v.t[2] = c.w;
-  v.centre[0] = d.x; v.centre[1] = d.y; v.centre[2] = d.z; v.comb = d.w;
-  v.rt_hi = __float_as_uint(e.z); v.rt_lo = __float_as_uint(e.w);
+  v.centre[0] = d.x; v.centre[1] = d.y; v.centre[2] = d.z;
 }
 
-// One source view of one row: project, gather, metadata -> the 13 (hi, lo) column pairs of
+// One source view of one row: project, gather, metadata -> the 12 (hi, lo) column pairs of
 // the K block.  HWC != 0: compile-time map size, every gather address is base + immediate.
 // WANT_BITS (warp-uniform): also return the depth-valid / in-bounds bits of the overall mask.
 template <int TW, int HWC>
 __device__ __forceinline__ unsigned view_block(const RowCtx& rc, const ViewParams* __restrict__ vpp,
                                                const float4* __restrict__ view4, int Wrt, int H, int HWrt,
-                                               const Centre& ctr, bool want_bits, uint32_t (&hi)[13],
-                                               uint32_t (&lo)[13]) {
+                                               const Centre& ctr, bool want_bits, uint32_t (&hi)[kBlkCols],
+                                               uint32_t (&lo)[kBlkCols]) {
   const int W = TW ? TW : Wrt, HW = HWC ? HWC : HWrt;
   ViewRegs vr;
   load_view(vpp, vr);
@@ -283,8 +297,7 @@ __device__ __forceinline__ unsigned view_block(const RowCtx& rc, const ViewParam
   split_pack(mk, zp, hi[8], lo[8]);
   split_pack(dot * mk, ang, hi[9], lo[9]);
   split_pack(sx, sy, hi[10], lo[10]);
-  split_pack(sz, vr.comb, hi[11], lo[11]);
-  hi[12] = vr.rt_hi; lo[12] = vr.rt_lo;
+  split_pack(sz, 0.0f, hi[11], lo[11]);
   unsigned bits = 0;
   if (want_bits) {
     if (zp > 0.0f) bits |= 1u;
@@ -294,7 +307,7 @@ __device__ __forceinline__ unsigned view_block(const RowCtx& rc, const ViewParam
 }
 
 // The view-independent tail block: reference features | plane depth | n_cur | one | zeros
-__device__ __forceinline__ void tail_block(const RowCtx& rc, uint32_t (&hi)[13], uint32_t (&lo)[13]) {
+__device__ __forceinline__ void tail_block(const RowCtx& rc, uint32_t (&hi)[kBlkCols], uint32_t (&lo)[kBlkCols]) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     split_pack(rc.cur4[j].x, rc.cur4[j].y, hi[2 * j], lo[2 * j]);
@@ -304,7 +317,6 @@ __device__ __forceinline__ void tail_block(const RowCtx& rc, uint32_t (&hi)[13],
   split_pack(rc.cy, rc.cz, hi[9], lo[9]);
   hi[10] = 0x00003C00u; lo[10] = 0u;      // (1.0, 0): the bias position
   hi[11] = 0u; lo[11] = 0u;
-  hi[12] = 0u; lo[12] = 0u;
 }
 
 // issue D (+)= A_hi W_hi + A_hi W_lo + A_lo W_hi over KSTEPS K steps of 16.
@@ -374,8 +386,8 @@ __device__ __forceinline__ void make_row(unsigned id, int row, int W, int H, int
 template <int TW, int HWC>
 __device__ __forceinline__ unsigned build_block(const RowCtx& rc, int blk, const float4* __restrict__ src4,
                                                 const ViewParams* __restrict__ views, int W, int H, int HW,
-                                                const Centre& ctr, bool want_bits, uint32_t (&hi)[13],
-                                                uint32_t (&lo)[13]) {
+                                                const Centre& ctr, bool want_bits, uint32_t (&hi)[kBlkCols],
+                                                uint32_t (&lo)[kBlkCols]) {
   if (blk < kViews)
     return view_block<TW, HWC>(rc, views + (rc.b * kViews + blk),
                                src4 + ((size_t)(rc.b * kViews + blk) * 4) * HW, W, H, HW, ctr, want_bits, hi, lo);
@@ -388,19 +400,20 @@ __global__ void __launch_bounds__(kThreads, 1)
 mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __restrict__ src4,
               const ViewParams* __restrict__ views, const FrameParams* __restrict__ frames,
               const float* __restrict__ planes, const uint8_t* __restrict__ image,
-              float* __restrict__ cost, uint8_t* __restrict__ mask_out, unsigned num_tiles) {
+              const float* __restrict__ frame_bias, float* __restrict__ cost, uint8_t* __restrict__ mask_out,
+              unsigned num_tiles) {
   SRCV_DYNAMIC_SMEM_ALIGNED(uint8_t, smem, 1024);
   __shared__ uint32_t s_tmem_base;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  uint64_t* bar_a1_full = bars + 0;   // workers -> MMA: A1 of a tile is in TMEM               (512 arrivals)
-  uint64_t* bar_mma1 = bars + 1;      // layer-1 MMAs done: DA holds D1, A1 is free           (commit)
-  uint64_t* bar_a2_full = bars + 2;   // workers -> MMA: A2 written over D1                   (512 arrivals)
-  uint64_t* bar_mma2 = bars + 3;      // layer-2 MMAs done: D2 ready, DA free                 (commit)
-  uint64_t* bar_d2_free = bars + 4;   // workers done reading D2                              (512 arrivals)
-  uint64_t* bar_e2 = bars + 5;        // layer-3 partial dots are in shared memory            (512 arrivals)
-  uint64_t* bar_img = bars + 6;       // weight image landed in shared memory (bulk copies)
+  // Barriers of a BUFFER (a1_full, d2_free) exist once per A1 buffer and complete every second
+  // tile: their waiters can lag two tiles, which a single phase bit could not tell apart.
+  uint64_t* bar_a1_full = bars + 0;   // [2] builders -> MMA: A1 of a tile is in TMEM          (384 arrivals)
+  uint64_t* bar_d2_free = bars + 2;   // [2] epilogues done reading D2: the buffer is free     (128 arrivals)
+  uint64_t* bar_mma1 = bars + 4;      // layer-1 MMAs done: DA holds D1                       (commit)
+  uint64_t* bar_a2_full = bars + 5;   // epilogues -> MMA: A2 written over D1                 (128 arrivals)
+  uint64_t* bar_mma2 = bars + 6;      // layer-2 MMAs done: D2 ready, DA free                 (commit)
+  uint64_t* bar_img = bars + 7;       // weight image landed in shared memory (bulk copies)
   uint8_t* sflag = smem + kOffFlag;
-  float* spart = reinterpret_cast<float*>(smem + kOffPart);
   const float* svec = reinterpret_cast<const float*>(smem + kOffVec);
 
   // The warp index goes through a shuffle broadcast so that ptxas knows the role branches are
@@ -415,12 +428,13 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
   // ---- one-time setup ----------------------------------------------------------------
   if (tid == 0) {
     mbar_init(bar_img, 1);
-    mbar_init(bar_a1_full, kWorkers);
+    mbar_init(bar_a1_full, kBuilders);
+    mbar_init(bar_a1_full + 1, kBuilders);
+    mbar_init(bar_d2_free, kEpis);
+    mbar_init(bar_d2_free + 1, kEpis);
     mbar_init(bar_mma1, 1);
-    mbar_init(bar_a2_full, kWorkers);
+    mbar_init(bar_a2_full, kEpis);
     mbar_init(bar_mma2, 1);
-    mbar_init(bar_d2_free, kWorkers);
-    mbar_init(bar_e2, kWorkers);
     mbar_fence_init();
   }
   if (warp == kMmaWarp) tmem_alloc(&s_tmem_base, kTmemCols);
@@ -454,97 +468,119 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
   auto tile_id = [&](unsigned j) { return blockIdx.x + j * gridDim.x; };
 #endif
 
-  if (warp < kWorkWarps) {
-    // =============================== row workers =========================================
+  if (warp < kBuildWarps) {
+    // =============================== builders ============================================
+    // Twelve warps: three threads per row (slot = warp / 4), each building a contiguous range of
+    // K blocks — slots 0 and 1 three source views each, slot 2 the last view and the tail.  With
+    // two A1 buffers they run up to a whole tile ahead of the tensor pipe: buffer t & 1 is free
+    // again once the layer-2 epilogue of tile t - 2 has read its accumulator out of it.
 #ifndef SRCV_TC_NO_SETMAXNREG
-    reg_inc<kRegsWorker>();
+    reg_inc<kRegsBuild>();
 #endif
-    const int row = tid & (kRows - 1), q = tid >> 7;
+    const int row = (warp & 3) * 32 + lane, slot = warp >> 2;
     const Centre ctr(W, H);
-    const int blk0 = 2 * q, blk1 = 2 * q + 1;   // q = 3: view 6 and the tail block (7)
+    const int blk_first = 3 * slot, blk_count = (slot < 2) ? 3 : 2;
     const bool masks = mask_out != nullptr;
     RowCtx rc;
-    uint32_t hi[13], lo[13];
-    long long out_cur = -1;
-    bool last_cur = false;
-    if (n_local > 0) {
-      // prologue: the first tile's A operand (its columns are free)
-      make_row<PER_PIXEL>(tile_id(0), row, W, H, HW, D, nd, tiles_x, tiles_xy, ctr, cur4g, frames, planes, rc);
+    uint32_t hi[kBlkCols], lo[kBlkCols];
+    for (unsigned it = 0; it < n_local; ++it) {
+      const uint32_t buf = it & 1u, use = it >> 1;       // use-th tile of this buffer
+      make_row<PER_PIXEL>(tile_id(it), row, W, H, HW, D, nd, tiles_x, tiles_xy, ctr, cur4g, frames, planes, rc);
       const bool wb = masks && rc.last_plane;
-      unsigned bits = build_block<TW, HWC>(rc, blk0, src4, views, W, H, HW, ctr, wb, hi, lo);
-      store_block(lane_base, (uint32_t)(13 * blk0), hi, lo);
-      bits |= build_block<TW, HWC>(rc, blk1, src4, views, W, H, HW, ctr, wb, hi, lo);
-      store_block(lane_base, (uint32_t)(13 * blk1), hi, lo);
-      if (wb) sflag[(0 * 4 + q) * kRows + row] = (uint8_t)bits;
+      const uint32_t a1_lane = lane_base + kColA1 + buf * kA1Stride;
+      unsigned bits = build_block<TW, HWC>(rc, blk_first, src4, views, W, H, HW, ctr, wb, hi, lo);
+      if (use > 0) {
+        mbar_wait(bar_d2_free + buf, (use - 1) & 1u);    // tile it - 2 is completely out of this buffer
+        fence_after_sync();
+      }
+      store_block(a1_lane, (uint32_t)(kBlkCols * blk_first), hi, lo);
+#pragma unroll 1
+      for (int j = 1; j < blk_count; ++j) {
+        bits |= build_block<TW, HWC>(rc, blk_first + j, src4, views, W, H, HW, ctr, wb, hi, lo);
+        store_block(a1_lane, (uint32_t)(kBlkCols * (blk_first + j)), hi, lo);
+      }
+      // Mask bits of this tile live with its buffer: the epilogue warp reads them before its
+      // bar_d2_free arrival for this tile, and the next store into the slot (tile it + 2) follows
+      // this thread's wait on exactly that barrier phase.
+      if (wb) sflag[(buf * 3 + slot) * kRows + row] = (uint8_t)bits;
       wait_st();
       fence_before_sync();
-      mbar_arrive(bar_a1_full);
-      out_cur = rc.out;
-      last_cur = rc.last_plane;
+      mbar_arrive(bar_a1_full + buf);
     }
+  } else if (warp < kBuildWarps + kEpiWarps) {
+    // =============================== epilogues ===========================================
+    // Four warps, one thread per row.  Layer-1 epilogue: per-frame pose bias, LeakyReLU, (hi, lo)
+    // split, layer-2 operand written IN PLACE over the accumulator, 32 columns at a time (a
+    // chunk's 32 fp32 columns become its 16 hi + 16 lo operand columns).  Layer-2 epilogue: bias,
+    // LeakyReLU and the 128 -> 1 layer as one dot product per row — no cross-thread reduction.
+#ifndef SRCV_TC_NO_SETMAXNREG
+    reg_inc<kRegsEpi>();
+#endif
+    const int row = (warp & 3) * 32 + lane;
+    const bool masks = mask_out != nullptr;
     for (unsigned it = 0; it < n_local; ++it) {
-      const uint32_t par = it & 1u;
-      const bool has_next = it + 1 < n_local;
-      unsigned nbits = 0;
-      bool nwb = false;
-      if (has_next) {
-        // first K block of the NEXT tile, built while this tile's layer-1 MMAs run
-        make_row<PER_PIXEL>(tile_id(it + 1), row, W, H, HW, D, nd, tiles_x, tiles_xy, ctr, cur4g, frames, planes, rc);
-        nwb = masks && rc.last_plane;
-        nbits = build_block<TW, HWC>(rc, blk0, src4, views, W, H, HW, ctr, nwb, hi, lo);
+      const uint32_t par = it & 1u, buf = it & 1u;
+      // where this row's cost goes (integer part of make_row)
+      long long out;
+      bool last_plane;
+      int b;
+      {
+        const unsigned id = tile_id(it);
+        const int d0 = (int)(id % nd) * kTileD;
+        const unsigned r = id / nd, txy = r % tiles_xy;
+        b = (int)(r / tiles_xy);
+        const int x0 = (int)(txy % tiles_x) * kTileW, y0 = (int)(txy / tiles_x) * kTileH;
+        const int rx = row & (kTileW - 1), ry = (row >> 4) & (kTileH - 1), dd = row >> 5;
+        const int d = d0 + dd;
+        const bool active = (x0 + rx < W) && (y0 + ry < H) && (d < D);
+        out = active ? ((long long)b * D + d) * HW + ((y0 + ry) * W + (x0 + rx)) : -1;
+        last_plane = (d == D - 1);
       }
-      // ---- layer-1 epilogue on columns [32q, 32q+32): LeakyReLU, (hi, lo), A2 IN PLACE
+      const float4* pb4 = reinterpret_cast<const float4*>(frame_bias + (size_t)b * kN);
       mbar_wait(bar_mma1, par);
       fence_after_sync();
-      // Mask bits of THIS tile.  The four quarters wrote them before their bar_a1_full arrival,
-      // so they are visible once bar_mma1 has completed; read here — before this thread's own
-      // bar_a1_full arrival for the next tile — the read is ordered before the store of the tile
-      // after next into the same parity slot (that store follows a bar_mma1 wait whose MMAs
-      // need every worker's bar_a1_full arrival).
       unsigned tile_bits = 0;
-      if (q == 0 && masks && last_cur) {
-        const uint8_t* fl = sflag + par * 4 * kRows + row;
-        tile_bits = fl[0] | fl[kRows] | fl[2 * kRows] | fl[3 * kRows];
+      if (masks && last_plane) {
+        const uint8_t* fl = sflag + buf * 3 * kRows + row;
+        tile_bits = fl[0] | fl[kRows] | fl[2 * kRows];
       }
-      {
+#pragma unroll 1
+      for (int c = 0; c < kN; c += 32) {
         uint32_t r[32];
-        ld_x32(lane_base + kColDA + 32 * q, r);
+        ld_x32(lane_base + kColDA + c, r);
         wait_ld();
         uint32_t ehi[16], elo[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          split_pack(leaky(__uint_as_float(r[2 * j])), leaky(__uint_as_float(r[2 * j + 1])), ehi[j], elo[j]);
-        st_x16(lane_base + kColDA + 32 * q, ehi);
-        st_x16(lane_base + kColDA + 32 * q + 16, elo);
+        for (int j = 0; j < 16; j += 2) {
+          const float4 pb = __ldg(pb4 + (c + 2 * j) / 4);      // per-frame pose bias (x16, like the accumulator)
+          split_pack(leaky(__uint_as_float(r[2 * j]) + pb.x), leaky(__uint_as_float(r[2 * j + 1]) + pb.y), ehi[j], elo[j]);
+          split_pack(leaky(__uint_as_float(r[2 * j + 2]) + pb.z), leaky(__uint_as_float(r[2 * j + 3]) + pb.w), ehi[j + 1], elo[j + 1]);
+        }
+        st_x16(lane_base + kColDA + c, ehi);
+        st_x16(lane_base + kColDA + c + 16, elo);
       }
       wait_st();
       fence_before_sync();
       mbar_arrive(bar_a2_full);
-      // ---- the rest of the next tile's A operand (A1 is free: layer 1 of this tile is done)
-      if (has_next) {
-        store_block(lane_base, (uint32_t)(13 * blk0), hi, lo);
-        nbits |= build_block<TW, HWC>(rc, blk1, src4, views, W, H, HW, ctr, nwb, hi, lo);
-        store_block(lane_base, (uint32_t)(13 * blk1), hi, lo);
-        if (nwb) sflag[((par ^ 1u) * 4 + q) * kRows + row] = (uint8_t)nbits;
-        wait_st();
-        fence_before_sync();
-        mbar_arrive(bar_a1_full);
-      }
-      // ---- layer-2 epilogue on columns [32q, 32q+32): bias + LeakyReLU, 128 -> 1 partial dot
+      // ---- layer-2 epilogue: the accumulator sits in the first 128 columns of this tile's A1 buffer
       mbar_wait(bar_mma2, par);
       fence_after_sync();
+      const uint32_t d2_lane = lane_base + kColA1 + buf * kA1Stride;
       float acc0 = 0.f, acc1 = 0.f;
-      {
+#pragma unroll 1
+      for (int c = 0; c < kN; c += 32) {
         uint32_t r[32];
-        ld_x32(lane_base + kColD2 + 32 * q, r);
+        ld_x32(d2_lane + c, r);
         wait_ld();
-        fence_before_sync();
-        mbar_arrive(bar_d2_free);     // D2 is in registers: the next tile's layer 2 may overwrite it
+        if (c == kN - 32) {
+          fence_before_sync();
+          mbar_arrive(bar_d2_free + buf);   // the buffer is free: the builders may write tile it + 2 into it
+        }
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 bb = *reinterpret_cast<const float4*>(svec + 32 * q + j);
-          const float4 wa = *reinterpret_cast<const float4*>(svec + kN + 32 * q + j);
-          const float4 wn = *reinterpret_cast<const float4*>(svec + 2 * kN + 32 * q + j);
+          const float4 bb = *reinterpret_cast<const float4*>(svec + c + j);
+          const float4 wa = *reinterpret_cast<const float4*>(svec + kN + c + j);
+          const float4 wn = *reinterpret_cast<const float4*>(svec + 2 * kN + c + j);
           const float h0 = fmaf(__uint_as_float(r[j + 0]), kUnscale2, bb.x);
           const float h1 = fmaf(__uint_as_float(r[j + 1]), kUnscale2, bb.y);
           const float h2 = fmaf(__uint_as_float(r[j + 2]), kUnscale2, bb.z);
@@ -555,25 +591,14 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
           acc1 = fmaf(wn.w, fabsf(h3), fmaf(wa.w, h3, acc1));
         }
       }
-      spart[(par * 4 + q) * kRows + row] = acc0 + acc1;
-      mbar_arrive(bar_e2);
-      if (q == 0) {
-        // fixed-order reduction of the four quarters (deterministic), bias, store
-        mbar_wait(bar_e2, par);
-        const float* sp = spart + par * 4 * kRows + row;
-        const float total = ((sp[0] + sp[kRows]) + sp[2 * kRows]) + sp[3 * kRows];
-        if (out_cur >= 0) {
-          cost[out_cur] = total + svec[3 * kN];
-          if (masks && last_cur) {
-            // overall mask of the LAST plane (reference :625-637): any view in front AND any view
-            // inside the 2-pixel border, independently
-            const long long bb = out_cur / ((long long)D * HW);
-            mask_out[bb * HW + (out_cur - (bb * D + (D - 1)) * HW)] = (tile_bits == 3u) ? 1 : 0;
-          }
+      if (out >= 0) {
+        cost[out] = (acc0 + acc1) + svec[3 * kN];
+        if (masks && last_plane) {
+          // overall mask of the LAST plane (reference :625-637): any view in front AND any view
+          // inside the 2-pixel border, independently
+          mask_out[(size_t)b * HW + (out - ((long long)b * D + (D - 1)) * HW)] = (tile_bits == 3u) ? 1 : 0;
         }
       }
-      out_cur = rc.out;
-      last_cur = rc.last_plane;
     }
   } else {
 #ifndef SRCV_TC_NO_SETMAXNREG
@@ -583,23 +608,23 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
       // =============================== MMA issuer ==========================================
       const uint32_t sbase = smem_u32(smem);
       for (unsigned it = 0; it < n_local; ++it) {
-        const uint32_t par = it & 1u;
-        mbar_wait(bar_a1_full, par);             // A1 of this tile is in TMEM
+        const uint32_t par = it & 1u, buf = it & 1u, use = it >> 1;
+        const uint32_t a1 = tmem_base + kColA1 + buf * kA1Stride;
+        mbar_wait(bar_a1_full + buf, use & 1u);   // A1 of this tile is in TMEM
         fence_after_sync();
         // DA is free: the layer-2 MMAs of the previous tile (its last readers) were issued before
         // these and the tensor pipe executes this thread's MMAs in order.
         if (lane == 0) {
-          issue_layer<kK1 / 16, false>(tmem_base + kColDA, tmem_base + kColA1Hi, kColA1Lo - kColA1Hi,
-                                       sbase + kOffW1Hi, sbase + kOffW1Lo);
+          issue_layer<kK1 / 16, false>(tmem_base + kColDA, a1, kA1LoOff, sbase + kOffW1Hi, sbase + kOffW1Lo);
           mma_commit(bar_mma1);
         }
         __syncwarp();
         mbar_wait(bar_a2_full, par);             // A2 written over D1
-        mbar_wait(bar_d2_free, par ^ 1u);        // previous tile's D2 has been read
         fence_after_sync();
+        // D2 goes into this tile's own A1 buffer: its layer-1 MMAs (just above, same in-order
+        // pipe) are the last readers, and the builders do not touch it before bar_d2_free.
         if (lane == 0) {
-          issue_layer<kK2 / 16, true>(tmem_base + kColD2, tmem_base + kColDA, 16u,
-                                      sbase + kOffW2Hi, sbase + kOffW2Lo);
+          issue_layer<kK2 / 16, true>(a1, tmem_base + kColDA, 16u, sbase + kOffW2Hi, sbase + kOffW2Lo);
           mma_commit(bar_mma2);
         }
         __syncwarp();
@@ -702,7 +727,9 @@ bool mlp_tc_supported(const srcv_shape& s, const srcv_mlp_weights& w) {
          (long long)s.H * s.W < (1ll << 26);
 }
 
-size_t mlp_tc_extra_bytes() { return (kImageBytes + 255) & ~(size_t)255; }
+static size_t image_bytes_aligned() { return (kImageBytes + 255) & ~(size_t)255; }
+// workspace tail of the tensor-core variant: [weight image | per-frame pose bias (B x 128 floats)]
+size_t mlp_tc_extra_bytes(const srcv_shape& s) { return image_bytes_aligned() + (((size_t)s.B * kN * 4 + 255) & ~(size_t)255); }
 size_t mlp_tc_image_bytes() { return kImageBytes; }
 
 cudaError_t launch_mlp_tc_pack(const srcv_mlp_weights& w, void* image, cudaStream_t stream) {
@@ -722,6 +749,10 @@ cudaError_t launch_mlp_tc(const srcv_shape& s, const float* cur, const Workspace
     if (err != cudaSuccess) return err;
     image = reinterpret_cast<const uint8_t*>(ws.extra);
   }
+  // the 21 pose measures enter layer 1 as a per-frame bias (views were written by the prep pass)
+  float* frame_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws.extra) + image_bytes_aligned());
+  SRCV_LAUNCH(tc_frame_bias_kernel, s.B, kN, 0, stream, w, ws.views, frame_bias);
+  note_launch();
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -738,7 +769,8 @@ cudaError_t launch_mlp_tc(const srcv_shape& s, const float* cur, const Workspace
                                (int)kSmemBytes);                                                      \
     if (err != cudaSuccess) return err;                                                               \
     SRCV_LAUNCH((mlp_tc_kernel<PP, TW_, TH_>), grid, kThreads, kSmemBytes, stream,                    \
-                s, cur4, src4, ws.views, ws.frames, planes, image, cost, mask, (unsigned)num_tiles);  \
+                s, cur4, src4, ws.views, ws.frames, planes, image, frame_bias, cost, mask,            \
+                (unsigned)num_tiles);                                                                 \
   } while (0)
 #define SRCV_TC_SIZES(PP)                                                   \
   if (s.W == 160 && s.H == 120) SRCV_TC_LAUNCH(PP, 160, 120);               \

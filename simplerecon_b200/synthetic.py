@@ -195,3 +195,42 @@ def make_tsdf_case(seed: int = 0, frames: int = 2, voxel_size: float = 0.04, hei
     bounds = {"xmin": -pad, "xmax": rx + pad, "ymin": -pad, "ymax": ry + pad, "zmin": -pad, "zmax": rz + pad}
     return dict(depth=depth, cam_T_world=torch.stack(Es), K=K.float().repeat(frames, 1, 1), mask=mask,
                 bounds=bounds, voxel_size=voxel_size, max_depth=3.0)
+
+
+def make_mvs_scene(seed: int = 0, frames: int = 8, height: int = 96, width: int = 128, room=(4.0, 3.0, 2.6),
+                   noise: float = 0.005) -> dict:
+    """A synthetic scan for the multi-view depth-consistency fusion (reference
+    tools/torch_point_cloud_fusion.py): `frames` views of a box-shaped room from nearby poses (so the
+    frusta overlap), each with its analytically ray-cast depth map (pixel (x, y) is the ray through
+    integer coordinates, as the fuser's un-projection assumes, :29-35), 3x3 intrinsics, world->camera
+    poses and random uint8 images.  A few depth pixels are zeroed (invalid predictions)."""
+    g = torch.Generator().manual_seed(9876 + seed)
+    rx, ry, rz = room
+    fx, fy = SCANNET_FX * width / 640.0, SCANNET_FY * height / 480.0
+    K = torch.eye(3, dtype=torch.float64)
+    K[0, 0], K[1, 1], K[0, 2], K[1, 2] = fx, fy, SCANNET_CX * width / 640.0, SCANNET_CY * height / 480.0
+    v, u = torch.meshgrid(torch.arange(height, dtype=torch.float64), torch.arange(width, dtype=torch.float64),
+                          indexing="ij")
+    rays_cam = torch.stack([(u - K[0, 2]) / fx, (v - K[1, 2]) / fy, torch.ones_like(u)], -1)
+    centre = torch.tensor([rx, ry, rz], dtype=torch.float64) * 0.5
+    base_axis = torch.randn(3, generator=g, dtype=torch.float64)
+    base_axis = base_axis / base_axis.norm()
+    base_R = _axis_angle(base_axis[None], torch.rand(1, generator=g, dtype=torch.float64) * 3.0)[0]
+    depths, Ps = [], []
+    for _ in range(frames):
+        pos = centre + 0.35 * (torch.rand(3, generator=g, dtype=torch.float64) - 0.5) * torch.tensor([rx, ry, rz])
+        ax = torch.randn(3, generator=g, dtype=torch.float64)
+        Rwc = base_R @ _axis_angle((ax / ax.norm())[None], torch.rand(1, generator=g, dtype=torch.float64) * 0.35)[0]
+        d = rays_cam @ Rwc.T
+        lo, hi = -pos, torch.tensor([rx, ry, rz], dtype=torch.float64) - pos
+        t = torch.where(d > 0, hi / d.clamp_min(1e-12), lo / d.clamp_max(-1e-12))
+        depth = t.min(-1).values + noise * torch.randn(height, width, generator=g, dtype=torch.float64)
+        depth[torch.rand(height, width, generator=g) < 0.02] = 0.0
+        depths.append(depth.float())
+        E = torch.eye(4, dtype=torch.float64)
+        E[:3, :3] = Rwc.T
+        E[:3, 3] = -(Rwc.T @ pos)
+        Ps.append(E.float())
+    images = torch.randint(0, 256, (frames, height, width, 3), generator=g, dtype=torch.uint8)
+    return dict(depths=torch.stack(depths), cam_T_world=torch.stack(Ps), K=K.float().repeat(frames, 1, 1),
+                images=images)
