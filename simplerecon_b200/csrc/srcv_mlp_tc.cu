@@ -494,10 +494,16 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
         fence_after_sync();
       }
       store_block(a1_lane, (uint32_t)(kBlkCols * blk_first), hi, lo);
+#ifdef SRCV_TC_UNROLL_BLOCKS
+#pragma unroll
+#else
 #pragma unroll 1
-      for (int j = 1; j < blk_count; ++j) {
-        bits |= build_block<TW, HWC>(rc, blk_first + j, src4, views, W, H, HW, ctr, wb, hi, lo);
-        store_block(a1_lane, (uint32_t)(kBlkCols * (blk_first + j)), hi, lo);
+#endif
+      for (int j = 1; j < 3; ++j) {
+        if (j < blk_count) {
+          bits |= build_block<TW, HWC>(rc, blk_first + j, src4, views, W, H, HW, ctr, wb, hi, lo);
+          store_block(a1_lane, (uint32_t)(kBlkCols * (blk_first + j)), hi, lo);
+        }
       }
       // Mask bits of this tile live with its buffer: the epilogue warp reads them before its
       // bar_d2_free arrival for this tile, and the next store into the slot (tile it + 2) follows
@@ -544,20 +550,27 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
         const uint8_t* fl = sflag + buf * 3 * kRows + row;
         tile_bits = fl[0] | fl[kRows] | fl[2 * kRows];
       }
+      // 64 columns per step: two TMEM loads in flight per wait, twice the independent work per
+      // dependent chain (this stage is a single warp per scheduler on the tensor pipe's critical path)
 #pragma unroll 1
-      for (int c = 0; c < kN; c += 32) {
-        uint32_t r[32];
+      for (int c = 0; c < kN; c += 64) {
+        uint32_t r[64];
         ld_x32(lane_base + kColDA + c, r);
+        ld_x32(lane_base + kColDA + c + 32, r + 32);
         wait_ld();
-        uint32_t ehi[16], elo[16];
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          const float4 pb = __ldg(pb4 + (c + 2 * j) / 4);      // per-frame pose bias (x16, like the accumulator)
-          split_pack(leaky(__uint_as_float(r[2 * j]) + pb.x), leaky(__uint_as_float(r[2 * j + 1]) + pb.y), ehi[j], elo[j]);
-          split_pack(leaky(__uint_as_float(r[2 * j + 2]) + pb.z), leaky(__uint_as_float(r[2 * j + 3]) + pb.w), ehi[j + 1], elo[j + 1]);
+        for (int h = 0; h < 2; ++h) {
+          uint32_t ehi[16], elo[16];
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const float4 pb = __ldg(pb4 + (c + 32 * h + 2 * j) / 4);   // per-frame pose bias (x16, like the accumulator)
+            const uint32_t* q = r + 32 * h + 2 * j;
+            split_pack(leaky(__uint_as_float(q[0]) + pb.x), leaky(__uint_as_float(q[1]) + pb.y), ehi[j], elo[j]);
+            split_pack(leaky(__uint_as_float(q[2]) + pb.z), leaky(__uint_as_float(q[3]) + pb.w), ehi[j + 1], elo[j + 1]);
+          }
+          st_x16(lane_base + kColDA + c + 32 * h, ehi);
+          st_x16(lane_base + kColDA + c + 32 * h + 16, elo);
         }
-        st_x16(lane_base + kColDA + c, ehi);
-        st_x16(lane_base + kColDA + c + 16, elo);
       }
       wait_st();
       fence_before_sync();
@@ -568,16 +581,17 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
       const uint32_t d2_lane = lane_base + kColA1 + buf * kA1Stride;
       float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < kN; c += 32) {
-        uint32_t r[32];
+      for (int c = 0; c < kN; c += 64) {
+        uint32_t r[64];
         ld_x32(d2_lane + c, r);
+        ld_x32(d2_lane + c + 32, r + 32);
         wait_ld();
-        if (c == kN - 32) {
+        if (c == kN - 64) {
           fence_before_sync();
           mbar_arrive(bar_d2_free + buf);   // the buffer is free: the builders may write tile it + 2 into it
         }
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
+        for (int j = 0; j < 64; j += 4) {
           const float4 bb = *reinterpret_cast<const float4*>(svec + c + j);
           const float4 wa = *reinterpret_cast<const float4*>(svec + kN + c + j);
           const float4 wn = *reinterpret_cast<const float4*>(svec + 2 * kN + c + j);

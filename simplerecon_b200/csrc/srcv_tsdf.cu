@@ -75,12 +75,12 @@ template <int VEC>
 __global__ void __launch_bounds__(256)
 tsdf_integrate_kernel(TsdfParams p, const TsdfFrame* __restrict__ frames, const __half* __restrict__ depth,
                       const uint8_t* __restrict__ mask, __half* __restrict__ tsdf, __half* __restrict__ weights) {
-  const long long cols = (long long)p.X * p.Y * (p.Z / VEC);
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= cols) return;
-  const int zc = (int)(t % (p.Z / VEC));
-  const long long xy = t / (p.Z / VEC);
-  const int iy = (int)(xy % p.Y), ix = (int)(xy / p.Y);
+  // grid.y walks x; grid.x * blockDim.x covers the (y, z-column) plane: 32-bit index arithmetic only
+  // (64-bit div/mod of a flat voxel index cost more than the projection of an empty column)
+  const unsigned zcols = (unsigned)(p.Z / VEC);
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= zcols * (unsigned)p.Y) return;
+  const int zc = (int)(t % zcols), iy = (int)(t / zcols), ix = (int)blockIdx.y;
   const int z0 = zc * VEC;
   const size_t base = ((size_t)ix * p.Y + iy) * p.Z + z0;
   // world coordinates: fp32 origin + index * voxel_size, then half (tools/tsdf.py:99-110, :92)
@@ -210,10 +210,11 @@ cudaError_t launch_tsdf_integrate(const srcv_tsdf_volume& v, const srcv_tsdf_fra
     const __half* depth = reinterpret_cast<const __half*>(f.depth) + (size_t)b0 * f.H * f.W;
     const uint8_t* mask = f.depth_mask ? f.depth_mask + (size_t)b0 * f.H * f.W : nullptr;
     const bool vec = (v.Z % kVec) == 0 && ((reinterpret_cast<uintptr_t>(tsdf) | reinterpret_cast<uintptr_t>(weights)) & 15u) == 0;
-    const long long cols = (long long)v.X * v.Y * (vec ? v.Z / kVec : v.Z);
-    const unsigned blocks = (unsigned)((cols + 255) / 256);
-    if (vec) SRCV_LAUNCH(tsdf_integrate_kernel<kVec>, blocks, 256, 0, stream, p, frames, depth, mask, tsdf, weights);
-    else SRCV_LAUNCH(tsdf_integrate_kernel<1>, blocks, 256, 0, stream, p, frames, depth, mask, tsdf, weights);
+    const long long plane = (long long)v.Y * (vec ? v.Z / kVec : v.Z);
+    if (plane > 2147483647ll || v.X > 65535) return cudaErrorInvalidValue;
+    const dim3 grid((unsigned)((plane + 255) / 256), (unsigned)v.X);
+    if (vec) SRCV_LAUNCH(tsdf_integrate_kernel<kVec>, grid, 256, 0, stream, p, frames, depth, mask, tsdf, weights);
+    else SRCV_LAUNCH(tsdf_integrate_kernel<1>, grid, 256, 0, stream, p, frames, depth, mask, tsdf, weights);
     note_launch();
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
