@@ -74,11 +74,12 @@ def algorithmic_bytes_per_frame(w, hero: bool, with_mask: bool) -> int:
 
 def mlp_flops_per_frame(w, issued: bool) -> float:
     """2 * D * HW * (F*128 + 128*128 + 128) algorithmic; `issued` counts what the
-    tcgen05 kernel actually issues: K padded to 208, three fp16 MMAs per product, layer 3 on SIMT."""
+    tcgen05 kernel actually issues: layer-1 K = 192 (the 21 pose measures enter as a per-frame bias,
+    182 live positions padded to 12 K-steps), three fp16 MMAs per product, layer 3 on SIMT."""
     rows = w.planes * w.height * w.width
     f_in = w.channels * (w.views + 1) + 10 * w.views + 4
     if issued:
-        return 2.0 * 3 * rows * (208 * 128 + 128 * 128)
+        return 2.0 * 3 * rows * (192 * 128 + 128 * 128)
     return 2.0 * rows * (f_in * 128 + 128 * 128 + 128)
 
 
@@ -128,7 +129,7 @@ def make_roofline(w, hero, frames, sweep_s, prep_s, step_s, variant, sm_mhz):
             "algorithmic_flops_per_launch": mlp_flops_per_frame(w, False) * frames,
             "issued_mma": {"achieved": tfi, "unit": "TFLOP/s", "frac_of_sustained": tfi / pk["tf_sustained"],
                            "frac_of_burst": tfi / pk["tf_burst"],
-                           "what": "fp16 hi/lo split: 3 MMAs per product, K1 padded 202->208"},
+                           "what": "fp16 hi/lo split: 3 MMAs per product, layer-1 K = 192"},
             "hbm": hbm, **common,
             "note": ("the metadata-MLP sweep is a dense contraction at ~7000 FLOP/B: tensor-bound; the HBM "
                      "fraction the metric names is reported under `hbm`"),

@@ -319,6 +319,21 @@ __device__ __forceinline__ void tail_block(const RowCtx& rc, uint32_t (&hi)[kBlk
   hi[11] = 0u; lo[11] = 0u;
 }
 
+// Optional per-tile timeline of CTA 0 (experiment builds only, -DSRCV_TC_TIMELINE): one lane of
+// each role stamps %globaltimer-free SM clocks at its phase boundaries; read back with
+// srcv_debug_read_timeline.  Not compiled into the shipped library.
+#ifdef SRCV_TC_TIMELINE
+constexpr int kTlTiles = 48, kTlEvents = 16;
+__device__ long long g_timeline[kTlTiles * kTlEvents];
+#define SRCV_TL(it, ev)                                                                            \
+  do {                                                                                             \
+    if (blockIdx.x == 0 && lane == 0 && (warp & 3) == 0 && (it) < (unsigned)kTlTiles)                \
+      g_timeline[(it) * kTlEvents + (ev)] = clock64();                                             \
+  } while (0)
+#else
+#define SRCV_TL(it, ev) do { } while (0)
+#endif
+
 // issue D (+)= A_hi W_hi + A_hi W_lo + A_lo W_hi over KSTEPS K steps of 16.
 // LAYER2: the operand sits where the layer-1 accumulator was — k-step ks reads the hi columns
 // 32 (ks / 2) + 8 (ks % 2) and the lo columns 16 further (see the layer-1 epilogue).
@@ -485,14 +500,17 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
     uint32_t hi[kBlkCols], lo[kBlkCols];
     for (unsigned it = 0; it < n_local; ++it) {
       const uint32_t buf = it & 1u, use = it >> 1;       // use-th tile of this buffer
+      SRCV_TL(it, 0);
       make_row<PER_PIXEL>(tile_id(it), row, W, H, HW, D, nd, tiles_x, tiles_xy, ctr, cur4g, frames, planes, rc);
       const bool wb = masks && rc.last_plane;
       const uint32_t a1_lane = lane_base + kColA1 + buf * kA1Stride;
       unsigned bits = build_block<TW, HWC>(rc, blk_first, src4, views, W, H, HW, ctr, wb, hi, lo);
+      SRCV_TL(it, 1);
       if (use > 0) {
         mbar_wait(bar_d2_free + buf, (use - 1) & 1u);    // tile it - 2 is completely out of this buffer
         fence_after_sync();
       }
+      SRCV_TL(it, 2);
       store_block(a1_lane, (uint32_t)(kBlkCols * blk_first), hi, lo);
 #ifdef SRCV_TC_UNROLL_BLOCKS
 #pragma unroll
@@ -512,6 +530,7 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
       wait_st();
       fence_before_sync();
       mbar_arrive(bar_a1_full + buf);
+      SRCV_TL(it, 3);
     }
   } else if (warp < kBuildWarps + kEpiWarps) {
     // =============================== epilogues ===========================================
@@ -545,6 +564,7 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
       const float4* pb4 = reinterpret_cast<const float4*>(frame_bias + (size_t)b * kN);
       mbar_wait(bar_mma1, par);
       fence_after_sync();
+      SRCV_TL(it, 4);
       unsigned tile_bits = 0;
       if (masks && last_plane) {
         const uint8_t* fl = sflag + buf * 3 * kRows + row;
@@ -575,9 +595,11 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
       wait_st();
       fence_before_sync();
       mbar_arrive(bar_a2_full);
+      SRCV_TL(it, 5);
       // ---- layer-2 epilogue: the accumulator sits in the first 128 columns of this tile's A1 buffer
       mbar_wait(bar_mma2, par);
       fence_after_sync();
+      SRCV_TL(it, 6);
       const uint32_t d2_lane = lane_base + kColA1 + buf * kA1Stride;
       float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll 1
@@ -589,6 +611,7 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
         if (c == kN - 64) {
           fence_before_sync();
           mbar_arrive(bar_d2_free + buf);   // the buffer is free: the builders may write tile it + 2 into it
+          SRCV_TL(it, 7);
         }
 #pragma unroll
         for (int j = 0; j < 64; j += 4) {
@@ -613,6 +636,7 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
           mask_out[(size_t)b * HW + (out - ((long long)b * D + (D - 1)) * HW)] = (tile_bits == 3u) ? 1 : 0;
         }
       }
+      SRCV_TL(it, 8);
     }
   } else {
 #ifndef SRCV_TC_NO_SETMAXNREG
@@ -626,6 +650,7 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
         const uint32_t a1 = tmem_base + kColA1 + buf * kA1Stride;
         mbar_wait(bar_a1_full + buf, use & 1u);   // A1 of this tile is in TMEM
         fence_after_sync();
+        SRCV_TL(it, 9);
         // DA is free: the layer-2 MMAs of the previous tile (its last readers) were issued before
         // these and the tensor pipe executes this thread's MMAs in order.
         if (lane == 0) {
@@ -633,8 +658,10 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
           mma_commit(bar_mma1);
         }
         __syncwarp();
+        SRCV_TL(it, 10);
         mbar_wait(bar_a2_full, par);             // A2 written over D1
         fence_after_sync();
+        SRCV_TL(it, 11);
         // D2 goes into this tile's own A1 buffer: its layer-1 MMAs (just above, same in-order
         // pipe) are the last readers, and the builders do not touch it before bar_d2_free.
         if (lane == 0) {
@@ -642,6 +669,7 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
           mma_commit(bar_mma2);
         }
         __syncwarp();
+        SRCV_TL(it, 12);
       }
     }
   }
@@ -799,6 +827,15 @@ cudaError_t launch_mlp_tc(const srcv_shape& s, const float* cur, const Workspace
   if (lowest) err = launch_argmax(s, cost, planes, per_pixel, lowest, stream);
   return err;
 }
+
+#ifdef SRCV_TC_TIMELINE
+}  // namespace srcv
+extern "C" int32_t srcv_debug_read_timeline(long long* host, int32_t n) {
+  const size_t bytes = sizeof(long long) * (size_t)(n < srcv::kTlTiles * srcv::kTlEvents ? n : srcv::kTlTiles * srcv::kTlEvents);
+  return (int32_t)cudaMemcpyFromSymbol(host, srcv::g_timeline, bytes);
+}
+namespace srcv {
+#endif
 
 // D (128 x 128) = A (128 x Kp) W^T (128 x Kp), Kp a multiple of 16 and <= 256; `scratch`
 // needs 2 * 128 * Kp halves.  Device pointers; test hook for tests/test_gpu_tc.py.
