@@ -92,7 +92,7 @@ constexpr uint32_t kOffW1Hi = 0, kOffW1Lo = kW1Bytes, kOffW2Hi = 2 * kW1Bytes,
                    kOffW2Lo = 2 * kW1Bytes + kW2Bytes, kOffVec = 2 * kW1Bytes + 2 * kW2Bytes;
 constexpr uint32_t kVecFloats = 3 * kN + 4;   // b2 | 0.505 w3 | 0.495 w3 | b3
 constexpr uint32_t kOffBar = kOffVec + kVecFloats * 4;
-constexpr uint32_t kOffFlag = kOffBar + 8 * 8;            // 8 mbarrier slots
+constexpr uint32_t kOffFlag = kOffBar + 12 * 8;           // 12 mbarrier slots (10 used)
 constexpr uint32_t kSmemBytes = kOffFlag + 2 * 3 * kRows;   // mask bits [parity][builder slot][row]
 // image = [W1hi | W1lo | W2hi | W2lo | vec] exactly as it sits in shared memory
 constexpr uint32_t kImageBytes = kOffBar;
@@ -334,18 +334,26 @@ __device__ long long g_timeline[kTlTiles * kTlEvents];
 #define SRCV_TL(it, ev) do { } while (0)
 #endif
 
-// issue D (+)= A_hi W_hi + A_hi W_lo + A_lo W_hi over KSTEPS K steps of 16.
+// issue D (+)= A_hi W_hi + A_hi W_lo + A_lo W_hi over the K steps [KS0, KS1) of 16, for the N
+// accumulator columns whose weight rows start at smem_hi / smem_lo (row n of a K chunk sits 16 n
+// bytes into it, so a column half is a start-address offset; the K-chunk stride stays kN * 16).
 // LAYER2: the operand sits where the layer-1 accumulator was — k-step ks reads the hi columns
 // 32 (ks / 2) + 8 (ks % 2) and the lo columns 16 further (see the layer-1 epilogue).
-template <int KSTEPS, bool LAYER2>
-__device__ __forceinline__ void issue_layer(uint32_t d, uint32_t a_base, uint32_t a_lo_off,
+#ifdef SRCV_TC_NO_SPLIT_HALVES   // experiment switch: whole-layer MMAs, epilogue and tensor pipe take turns
+constexpr bool kSplitHalves = false;
+#else
+constexpr bool kSplitHalves = true;
+#endif
+
+template <int N, int KS0, int KS1, bool LAYER2>
+__device__ __forceinline__ void issue_steps(uint32_t d, uint32_t a_base, uint32_t a_lo_off,
                                             uint32_t smem_hi, uint32_t smem_lo) {
-  constexpr uint32_t idesc = idesc_f16_f32(kRows, kN);
+  constexpr uint32_t idesc = idesc_f16_f32(kRows, N);
   constexpr uint32_t kLbo = kN * 16, kSbo = 128, kStepBytes = 2 * kLbo;  // two 8-wide K chunks per MMA
   // only the 14-bit start-address field changes from step to step
-  uint64_t bhi = smem_desc(smem_hi, kLbo, kSbo), blo = smem_desc(smem_lo, kLbo, kSbo);
+  uint64_t bhi = smem_desc(smem_hi + KS0 * kStepBytes, kLbo, kSbo), blo = smem_desc(smem_lo + KS0 * kStepBytes, kLbo, kSbo);
 #pragma unroll 1
-  for (int ks = 0; ks < KSTEPS; ++ks) {
+  for (int ks = KS0; ks < KS1; ++ks) {
     const uint32_t ahi = LAYER2 ? a_base + 32u * (uint32_t)(ks >> 1) + 8u * (uint32_t)(ks & 1)
                                 : a_base + 8u * (uint32_t)ks;
     const uint32_t alo = ahi + a_lo_off;
@@ -424,10 +432,13 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
   // tile: their waiters can lag two tiles, which a single phase bit could not tell apart.
   uint64_t* bar_a1_full = bars + 0;   // [2] builders -> MMA: A1 of a tile is in TMEM          (384 arrivals)
   uint64_t* bar_d2_free = bars + 2;   // [2] epilogues done reading D2: the buffer is free     (128 arrivals)
-  uint64_t* bar_mma1 = bars + 4;      // layer-1 MMAs done: DA holds D1                       (commit)
-  uint64_t* bar_a2_full = bars + 5;   // epilogues -> MMA: A2 written over D1                 (128 arrivals)
-  uint64_t* bar_mma2 = bars + 6;      // layer-2 MMAs done: D2 ready, DA free                 (commit)
-  uint64_t* bar_img = bars + 7;       // weight image landed in shared memory (bulk copies)
+  // Layer 1 runs as two 64-column halves so that the epilogue of the first half overlaps the MMAs
+  // of the second, and layer 2 as two K halves so that it starts on the first half's operand while
+  // the epilogue still converts the second: the tensor pipe and the epilogue warps stop taking turns.
+  uint64_t* bar_mma1 = bars + 4;      // [2] layer-1 MMAs of a column half done: DA half holds D1 (commit)
+  uint64_t* bar_a2_full = bars + 6;   // [2] epilogues -> MMA: A2 half written over its D1 half  (128 arrivals)
+  uint64_t* bar_mma2 = bars + 8;      // layer-2 MMAs done: D2 ready, DA free                 (commit)
+  uint64_t* bar_img = bars + 9;       // weight image landed in shared memory (bulk copies)
   uint8_t* sflag = smem + kOffFlag;
   const float* svec = reinterpret_cast<const float*>(smem + kOffVec);
 
@@ -448,7 +459,9 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
     mbar_init(bar_d2_free, kEpis);
     mbar_init(bar_d2_free + 1, kEpis);
     mbar_init(bar_mma1, 1);
+    mbar_init(bar_mma1 + 1, 1);
     mbar_init(bar_a2_full, kEpis);
+    mbar_init(bar_a2_full + 1, kEpis);
     mbar_init(bar_mma2, 1);
     mbar_fence_init();
   }
@@ -562,18 +575,15 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
         last_plane = (d == D - 1);
       }
       const float4* pb4 = reinterpret_cast<const float4*>(frame_bias + (size_t)b * kN);
-      mbar_wait(bar_mma1, par);
-      fence_after_sync();
-      SRCV_TL(it, 4);
-      unsigned tile_bits = 0;
-      if (masks && last_plane) {
-        const uint8_t* fl = sflag + buf * 3 * kRows + row;
-        tile_bits = fl[0] | fl[kRows] | fl[2 * kRows];
-      }
       // 64 columns per step: two TMEM loads in flight per wait, twice the independent work per
       // dependent chain (this stage is a single warp per scheduler on the tensor pipe's critical path)
 #pragma unroll 1
       for (int c = 0; c < kN; c += 64) {
+        if (kSplitHalves || c == 0) {
+          mbar_wait(bar_mma1 + (c >> 6), par);   // this column half of D1 is complete
+          fence_after_sync();
+          SRCV_TL(it, c ? 14 : 4);
+        }
         uint32_t r[64];
         ld_x32(lane_base + kColDA + c, r);
         ld_x32(lane_base + kColDA + c + 32, r + 32);
@@ -591,11 +601,19 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
           st_x16(lane_base + kColDA + c + 32 * h, ehi);
           st_x16(lane_base + kColDA + c + 32 * h + 16, elo);
         }
+        if (kSplitHalves || c == kN - 64) {
+          wait_st();
+          fence_before_sync();
+          mbar_arrive(bar_a2_full + (c >> 6));   // k-steps 4 (c / 64) .. + 3 of the layer-2 operand
+          SRCV_TL(it, c ? 5 : 13);
+        }
       }
-      wait_st();
-      fence_before_sync();
-      mbar_arrive(bar_a2_full);
-      SRCV_TL(it, 5);
+      // mask bits of the builders: visible since the bar_mma1 waits above (a1_full -> MMA -> commit)
+      unsigned tile_bits = 0;
+      if (masks && last_plane) {
+        const uint8_t* fl = sflag + buf * 3 * kRows + row;
+        tile_bits = fl[0] | fl[kRows] | fl[2 * kRows];
+      }
       // ---- layer-2 epilogue: the accumulator sits in the first 128 columns of this tile's A1 buffer
       mbar_wait(bar_mma2, par);
       fence_after_sync();
@@ -653,20 +671,45 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
         SRCV_TL(it, 9);
         // DA is free: the layer-2 MMAs of the previous tile (its last readers) were issued before
         // these and the tensor pipe executes this thread's MMAs in order.
-        if (lane == 0) {
-          issue_layer<kK1 / 16, false>(tmem_base + kColDA, a1, kA1LoOff, sbase + kOffW1Hi, sbase + kOffW1Lo);
-          mma_commit(bar_mma1);
-        }
-        __syncwarp();
-        SRCV_TL(it, 10);
-        mbar_wait(bar_a2_full, par);             // A2 written over D1
-        fence_after_sync();
-        SRCV_TL(it, 11);
-        // D2 goes into this tile's own A1 buffer: its layer-1 MMAs (just above, same in-order
-        // pipe) are the last readers, and the builders do not touch it before bar_d2_free.
-        if (lane == 0) {
-          issue_layer<kK2 / 16, true>(a1, tmem_base + kColDA, 16u, sbase + kOffW2Hi, sbase + kOffW2Lo);
-          mma_commit(bar_mma2);
+        if (kSplitHalves) {
+          if (elect_one()) {
+            issue_steps<kN / 2, 0, kK1 / 16, false>(tmem_base + kColDA, a1, kA1LoOff, sbase + kOffW1Hi, sbase + kOffW1Lo);
+            mma_commit(bar_mma1);
+            issue_steps<kN / 2, 0, kK1 / 16, false>(tmem_base + kColDA + kN / 2, a1, kA1LoOff,
+                                                    sbase + kOffW1Hi + (kN / 2) * 16, sbase + kOffW1Lo + (kN / 2) * 16);
+            mma_commit(bar_mma1 + 1);
+          }
+          __syncwarp();
+          SRCV_TL(it, 10);
+          mbar_wait(bar_a2_full, par);             // first half of A2 written over D1
+          fence_after_sync();
+          SRCV_TL(it, 11);
+          // D2 goes into this tile's own A1 buffer: its layer-1 MMAs (just above, same in-order
+          // pipe) are the last readers, and the builders do not touch it before bar_d2_free.
+          if (elect_one())
+            issue_steps<kN, 0, kK2 / 32, true>(a1, tmem_base + kColDA, 16u, sbase + kOffW2Hi, sbase + kOffW2Lo);
+          __syncwarp();
+          mbar_wait(bar_a2_full + 1, par);         // second half
+          fence_after_sync();
+          SRCV_TL(it, 15);
+          if (elect_one()) {
+            issue_steps<kN, kK2 / 32, kK2 / 16, true>(a1, tmem_base + kColDA, 16u, sbase + kOffW2Hi, sbase + kOffW2Lo);
+            mma_commit(bar_mma2);
+          }
+        } else {
+          if (elect_one()) {
+            issue_steps<kN, 0, kK1 / 16, false>(tmem_base + kColDA, a1, kA1LoOff, sbase + kOffW1Hi, sbase + kOffW1Lo);
+            mma_commit(bar_mma1);
+          }
+          __syncwarp();
+          SRCV_TL(it, 10);
+          mbar_wait(bar_a2_full + 1, par);         // A2 written over D1
+          fence_after_sync();
+          SRCV_TL(it, 11);
+          if (elect_one()) {
+            issue_steps<kN, 0, kK2 / 16, true>(a1, tmem_base + kColDA, 16u, sbase + kOffW2Hi, sbase + kOffW2Lo);
+            mma_commit(bar_mma2);
+          }
         }
         __syncwarp();
         SRCV_TL(it, 12);

@@ -111,6 +111,21 @@ __host__ __device__ constexpr uint32_t idesc_f16_f32(int M, int N) {
   return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// One thread of a CONVERGED warp, chosen by elect.sync: code guarded by this predicate is known
+// to ptxas to run in a single thread, so a tcgen05.mma inside it is emitted bare — under a
+// `lane == 0` branch every MMA is wrapped in an ELECT / branch loop of its own (six dependent
+// instructions per MMA, which made the 128 x 128 x 16 MMAs issue-bound at ~87 clk against a
+// 64 clk tensor-pipe floor; scripts/mma_probe.cu, profiles/r02_mma_probe.jsonl).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- MMA: D[tmem] (+)= A[tmem] * B[smem]^T ; issued by ONE thread -----------------------
 __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                        uint32_t accumulate) {

@@ -184,6 +184,9 @@ inline void mma_commit(uint64_t* bar) {
   detail::update(bar, 1, 0);
 }
 
+// elect.sync of a converged warp: the model always picks lane 0
+inline bool elect_one() { return (threadIdx.x & 31) == 0; }
+
 template <int N> inline void reg_inc() {}
 template <int N> inline void reg_dec() {}
 
