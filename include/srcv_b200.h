@@ -317,6 +317,38 @@ int32_t srcv_mvs_consistency_f32(const srcv_mvs_scan* scan, int32_t ref_index, f
                                  int32_t n_consistent, float* pts_avg, int32_t* n_valid, uint8_t* valid,
                                  void* workspace, size_t workspace_bytes, int32_t frames_ready, void* stream);
 
+/* ---- multi-view depth regression loss (training) ------------------------------------- *
+ * Replaces MVDepthLoss.forward of the reference (losses.py:180-208, with get_valid_mask :90-135
+ * and get_error_for_pair :138-178; called from experiment_modules/depth_model.py:477-485): for every
+ * source view, the whole-batch mean over valid pixels of |log s - log z|, s = the view's depth
+ * nearest-sampled where the GROUND-TRUTH depth projects, z = the depth of the PREDICTED point in
+ * that view; the loss is the mean over the views.  NaN terms are dropped (nanmean).  fp32, the
+ * reference's operation order.  All pointers DEVICE memory, dense:
+ *   depth_pred, cur_depth (B,1,H,W)   src_depth (B,K,1,H,W)
+ *   cur_invK, cur_world_T_cam (B,4,4)   src_K, src_cam_T_world (B,K,4,4)          K <= 16
+ * forward : loss (1 float) out; optional valid_mask (B,K,H,W) uint8 and src_depth_sampled
+ *           (B,K,H,W) float outputs = get_valid_mask of every view (NULL: not written).
+ * backward: grad_depth_pred (B,1,H,W) out = grad_loss[0] * d loss / d depth_pred; `workspace` must
+ *           be the one the forward call of the same arguments filled (it keeps the per-view counts).
+ * Deterministic: per-CTA partial sums reduced in a fixed order.                                 */
+typedef struct srcv_mvloss_args {
+  const float* depth_pred;
+  const float* cur_depth;
+  const float* src_depth;
+  const float* cur_invK;
+  const float* src_K;
+  const float* cur_world_T_cam;
+  const float* src_cam_T_world;
+  int32_t B, K, H, W;
+} srcv_mvloss_args;
+size_t srcv_mvloss_workspace_bytes(const srcv_mvloss_args* args);
+int32_t srcv_mvloss_forward_f32(const srcv_mvloss_args* args, float* loss, uint8_t* valid_mask,
+                                float* src_depth_sampled, void* workspace, size_t workspace_bytes,
+                                void* stream);
+int32_t srcv_mvloss_backward_f32(const srcv_mvloss_args* args, const float* grad_loss,
+                                 float* grad_depth_pred, const void* workspace, size_t workspace_bytes,
+                                 void* stream);
+
 /* ---- tuning / introspection ------------------------------------------- *
  * Selects the kernel variant used by the two forward calls on this thread's
  * next invocations (process-global).  0 = automatic choice.  Used by the tests

@@ -71,6 +71,11 @@ class MvsScan(C.Structure):
                 ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32)]
 
 
+class MvLossArgs(C.Structure):
+    _fields_ = [(n, _fp) for n in ("depth_pred", "cur_depth", "src_depth", "cur_invK", "src_K", "cur_world_T_cam",
+                                   "src_cam_T_world")] + [(n, C.c_int32) for n in ("B", "K", "H", "W")]
+
+
 # every symbol include/srcv_b200.h declares: (restype, argtypes)
 SYMBOLS = {
     "srcv_abi_version": (C.c_int32, []),
@@ -107,6 +112,9 @@ SYMBOLS = {
     "srcv_mvs_workspace_bytes": (C.c_size_t, [C.POINTER(MvsScan)]),
     "srcv_mvs_consistency_f32": (C.c_int32, [C.POINTER(MvsScan), C.c_int32, C.c_float, C.c_int32, _fp, _fp, _fp,
                                              _fp, C.c_size_t, C.c_int32, _fp]),
+    "srcv_mvloss_workspace_bytes": (C.c_size_t, [C.POINTER(MvLossArgs)]),
+    "srcv_mvloss_forward_f32": (C.c_int32, [C.POINTER(MvLossArgs), _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
+    "srcv_mvloss_backward_f32": (C.c_int32, [C.POINTER(MvLossArgs), _fp, _fp, _fp, C.c_size_t, _fp]),
     "srcv_set_variant": (C.c_int32, [C.c_int32]),
     "srcv_last_variant": (C.c_char_p, []),
     "srcv_launch_count": (C.c_uint64, []),

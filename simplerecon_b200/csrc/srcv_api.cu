@@ -479,6 +479,46 @@ int32_t srcv_mvs_consistency_f32(const srcv_mvs_scan* s, int32_t ref, float z_th
   return SRCV_OK;
 }
 
+static int32_t check_mvloss(const srcv_mvloss_args* a) {
+  if (!a) return fail(SRCV_ERR_NULL, "loss arguments are NULL");
+  if (!a->depth_pred || !a->cur_depth || !a->src_depth || !a->cur_invK || !a->src_K || !a->cur_world_T_cam ||
+      !a->src_cam_T_world)
+    return fail(SRCV_ERR_NULL, "a loss input pointer is NULL");
+  if (a->B <= 0 || a->K <= 0 || a->H <= 0 || a->W <= 0 || (long long)a->H * a->W > (1ll << 26) ||
+      (long long)a->B * a->K * a->H * a->W > (1ll << 40) || a->B > 65535)
+    return fail(SRCV_ERR_SHAPE, "bad loss shape B=%d K=%d H=%d W=%d", a->B, a->K, a->H, a->W);
+  if (a->K > mvloss_max_views())
+    return fail(SRCV_ERR_UNSUPPORTED, "at most %d source views per call (got %d)", mvloss_max_views(), a->K);
+  return SRCV_OK;
+}
+
+size_t srcv_mvloss_workspace_bytes(const srcv_mvloss_args* a) {
+  if (!a || a->B <= 0 || a->K <= 0 || a->H <= 0 || a->W <= 0) return 0;
+  return mvloss_workspace_bytes(*a);
+}
+
+int32_t srcv_mvloss_forward_f32(const srcv_mvloss_args* a, float* loss, uint8_t* valid_mask, float* sampled,
+                                void* workspace, size_t workspace_bytes, void* stream_) {
+  if (int32_t e = check_mvloss(a)) return e;
+  if (!loss) return fail(SRCV_ERR_NULL, "loss output pointer is NULL");
+  if (int32_t e = check_workspace(workspace, workspace_bytes, mvloss_workspace_bytes(*a))) return e;
+  g_last_variant.store("mvloss_forward_f32");
+  cudaError_t err = launch_mvloss_forward(*a, loss, valid_mask, sampled, workspace, static_cast<cudaStream_t>(stream_));
+  if (err != cudaSuccess) return cuda_fail(err, "mvloss_forward");
+  return SRCV_OK;
+}
+
+int32_t srcv_mvloss_backward_f32(const srcv_mvloss_args* a, const float* grad_loss, float* grad_depth_pred,
+                                 const void* workspace, size_t workspace_bytes, void* stream_) {
+  if (int32_t e = check_mvloss(a)) return e;
+  if (!grad_loss || !grad_depth_pred) return fail(SRCV_ERR_NULL, "grad_loss / grad_depth_pred is NULL");
+  if (int32_t e = check_workspace(const_cast<void*>(workspace), workspace_bytes, mvloss_workspace_bytes(*a))) return e;
+  g_last_variant.store("mvloss_backward_f32");
+  cudaError_t err = launch_mvloss_backward(*a, grad_loss, grad_depth_pred, workspace, static_cast<cudaStream_t>(stream_));
+  if (err != cudaSuccess) return cuda_fail(err, "mvloss_backward");
+  return SRCV_OK;
+}
+
 int32_t srcv_tc_selftest_f32(const float* A, const float* Wm, int32_t Kp, float* D, void* scratch,
                              void* stream) {
   if (!A || !Wm || !D || !scratch) return fail(SRCV_ERR_NULL, "selftest pointer is NULL");

@@ -109,6 +109,14 @@ cudaError_t launch_mvs_consistency(const srcv_mvs_scan& s, int ref, float z_thre
                                    float* pts_avg, int* n_valid, uint8_t* valid, void* workspace,
                                    bool frames_ready, cudaStream_t stream);
 
+// multi-view depth regression loss (csrc/srcv_mvloss.cu)
+int mvloss_max_views();
+size_t mvloss_workspace_bytes(const srcv_mvloss_args& a);
+cudaError_t launch_mvloss_forward(const srcv_mvloss_args& a, float* loss, uint8_t* valid, float* sampled,
+                                  void* workspace, cudaStream_t stream);
+cudaError_t launch_mvloss_backward(const srcv_mvloss_args& a, const float* grad_loss, float* grad_pred,
+                                   const void* workspace, cudaStream_t stream);
+
 // argmax over planes -> plane depth (used by variants that do not fuse it)
 cudaError_t launch_argmax(const srcv_shape& s, const float* cost, const float* planes,
                           bool per_pixel, float* lowest, cudaStream_t stream);

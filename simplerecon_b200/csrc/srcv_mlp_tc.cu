@@ -81,7 +81,18 @@ constexpr int kBuildWarps = 12, kEpiWarps = 4, kMmaWarp = 16;
 constexpr int kThreads = 20 * 32;
 constexpr int kBuilders = kBuildWarps * 32, kEpis = kEpiWarps * 32;
 constexpr int kRegsLaunch = 96;          // what ptxas allocates under __launch_bounds__(640, 1)
+#ifdef SRCV_TC_HALF_UNITS
+// Half-view units (below): a builder thread keeps the eight gathers of the NEXT unit in flight while
+// it converts the current one — two 32-register gather buffers — so the builders take 120 registers
+// and the epilogue warps work in 32-column steps within 96.
+constexpr bool kHalfUnits = true;
+constexpr int kRegsBuild = 120, kRegsEpi = 96, kRegsMma = 24;
+constexpr int kEpiStep = 32;
+#else
+constexpr bool kHalfUnits = false;
 constexpr int kRegsBuild = 112, kRegsEpi = 120, kRegsMma = 24;
+constexpr int kEpiStep = 64;
+#endif
 static_assert(kBuilders * kRegsBuild + kEpis * kRegsEpi + (kThreads - kBuilders - kEpis) * kRegsMma <= kThreads * kRegsLaunch,
               "setmaxnreg budget: increases must be covered by the decreases within the CTA's launch allocation");
 static_assert(kRegsBuild % 8 == 0 && kRegsEpi % 8 == 0 && kRegsMma % 8 == 0, "setmaxnreg takes multiples of 8");
@@ -107,6 +118,18 @@ __host__ __device__ inline uint32_t core_offset(int n, int k, int N) {
 // view) are NOT in K: they are constant per (frame, view), so their layer-1 contribution is a
 // per-frame bias vector (tc_frame_bias_kernel) added in the layer-1 epilogue.
 __host__ __device__ inline int ref_channel(int kk) {
+  if (kHalfUnits && kk < kViews * kBlk) {
+    // half-view units: a view block is two units of 12 K positions, unit h of view k =
+    //   8 warped features (channels 8h..8h+7) | partial dot over those channels | three measures:
+    //   h = 0: mask, z', ray angle      h = 1: n_src (3)
+    // The dot appears twice (both partial sums meet the same W1 column; the MMA adds them).
+    const int k = kk / kBlk, j = kk - k * kBlk, h = j / (kBlk / 2), i = j - h * (kBlk / 2);
+    const int base = kC * (kViews + 1);
+    if (i < 8) return k * kC + 8 * h + i;
+    if (i == 8) return base + 2 * kViews + 1 + k;          // dot
+    if (h == 0) return i == 9 ? base + k : (i == 10 ? base + kViews + k : base + 3 * kViews + 1 + k);
+    return base + 4 * kViews + 4 + 3 * k + (i - 9);        // n_src
+  }
   if (kk < kViews * kBlk) {
     const int k = kk / kBlk, j = kk - k * kBlk;
     if (j < kC) return k * kC + j;                       // warped features
@@ -319,6 +342,122 @@ __device__ __forceinline__ void tail_block(const RowCtx& rc, uint32_t (&hi)[kBlk
   hi[11] = 0u; lo[11] = 0u;
 }
 
+// ---- half-view units (-DSRCV_TC_HALF_UNITS) ---------------------------------------------------
+// A unit = one source view, channels 8h..8h+7: eight vector gathers, eight warped channels, the
+// partial dot over those channels and three of the view's six per-sample measures = 6 packed
+// columns.  The 14 units + the tail spread 5 / 5 / 4+tail over the three threads of a row (the
+// whole-view split was 3 / 3 / 1+tail views: the builders' critical path drops from 3 to 2.5 views),
+// and a unit is small enough to keep the NEXT unit's gathers in flight while this one is converted.
+constexpr int kUnitCols = kBlkCols / 2;     // 6
+constexpr int kUnits = 2 * kViews;          // 14; unit index 14 = the tail block
+
+// what the conversion of a unit needs once its gathers are under way
+struct UnitCtx {
+  float w00, w01, w10, w11;   // bilinear weights (zeros-padding taps: 0)
+  float mk, e0, e1, e2;       // depth validity of the view; the unit's three measures
+};
+
+// project, set the footprint up and ISSUE the unit's eight gathers (f: [tap][chunk of the half])
+template <int TW, int HWC>
+__device__ __forceinline__ unsigned unit_issue(const RowCtx& rc, int unit, const float4* __restrict__ src4,
+                                               const ViewParams* __restrict__ views, int Wrt, int H, int HWrt,
+                                               const Centre& ctr, bool want_bits, UnitCtx& uc, float4 (&f)[4][2]) {
+  const int W = TW ? TW : Wrt, HW = HWC ? HWC : HWrt;
+  const int k = unit >> 1, half = unit & 1;
+  const ViewParams* vpp = views + (rc.b * kViews + k);
+  const float4* view4 = src4 + ((size_t)(rc.b * kViews + k) * 4 + 2 * half) * HW;
+  ViewRegs vr;
+  load_view(vpp, vr);
+  const float ax = fmaf(vr.hx[0], rc.dxc, fmaf(vr.hy[0], rc.dyc, vr.a0[0]));
+  const float ay = fmaf(vr.hx[1], rc.dxc, fmaf(vr.hy[1], rc.dyc, vr.a0[1]));
+  const float az = fmaf(vr.hx[2], rc.dxc, fmaf(vr.hy[2], rc.dyc, vr.a0[2]));
+  float px, py, zp;
+  project_point(rc.dval, ax, ay, az, vr.t[0], vr.t[1], vr.t[2], px, py, zp);
+  const float x0f = floorf(px), y0f = floorf(py);
+  const float fx = px - x0f, fy = py - y0f;
+  const bool inside = x0f >= -(float)ctr.nx && x0f <= (float)(W - 2 - ctr.nx) &&
+                      y0f >= -(float)ctr.ny && y0f <= (float)(H - 2 - ctr.ny);
+  const bool interior = __all_sync(0xffffffffu, inside);
+  const float gx = 1.0f - fx, gy = 1.0f - fy;
+  uc.w00 = gx * gy; uc.w01 = fx * gy; uc.w10 = gx * fy; uc.w11 = fx * fy;
+  int o00, o01, o10, o11;
+  if (interior) {
+    o00 = ((int)y0f + ctr.ny) * W + ((int)x0f + ctr.nx);
+    o01 = o00 + 1; o10 = o00 + W; o11 = o00 + W + 1;
+  } else {
+    // border patches, branch-free: clamped (in-range) addresses, zero weights for padding taps
+    Taps tp;
+    bilinear_taps(px, py, W, H, ctr, tp);
+    const int cxa = min(max(tp.x0, 0), W - 1), cxb = min(max(tp.x0 + 1, 0), W - 1);
+    const int cya = min(max(tp.y0, 0), H - 1) * W, cyb = min(max(tp.y0 + 1, 0), H - 1) * W;
+    o00 = cya + cxa; o01 = cya + cxb; o10 = cyb + cxa; o11 = cyb + cxb;
+    uc.w00 = (tp.valid & 1u) ? uc.w00 : 0.f; uc.w01 = (tp.valid & 2u) ? uc.w01 : 0.f;
+    uc.w10 = (tp.valid & 4u) ? uc.w10 : 0.f; uc.w11 = (tp.valid & 8u) ? uc.w11 : 0.f;
+  }
+  {
+    const float4 *q0 = view4 + o00, *q1 = view4 + o01, *q2 = view4 + o10, *q3 = view4 + o11;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+#ifdef SRCV_TC_ABL_NOGATHER   // ablation build (wrong results): how much of a tile is gather latency?
+      f[0][j] = f[1][j] = f[2][j] = f[3][j] = make_float4(uc.w00, uc.w01, (float)(o00 + o11), (float)(o01 + o10 + (int)(size_t)q0));
+      (void)q1; (void)q2; (void)q3;
+#else
+      f[0][j] = __ldg(q0 + (size_t)j * HW);
+      f[1][j] = __ldg(q1 + (size_t)j * HW);
+      f[2][j] = __ldg(q2 + (size_t)j * HW);
+      f[3][j] = __ldg(q3 + (size_t)j * HW);
+#endif
+    }
+  }
+  // the view's measures (independent of the gathers): mask, z', ray angle | n_src
+  const float mk = zp > 0.0f ? 1.0f : 0.0f;
+  const float sx0 = rc.X - vr.centre[0], sy0 = rc.Y - vr.centre[1], sz0 = rc.Z - vr.centre[2];
+  const float is = inv_norm(fmaf(sx0, sx0, fmaf(sy0, sy0, sz0 * sz0)), kEpsNorm);
+  const float sx = sx0 * is, sy = sy0 * is, sz = sz0 * is;
+  const float i2 = inv_norm(fmaf(sx, sx, fmaf(sy, sy, sz * sz)), kEpsCos);
+  const float ang = fmaf(rc.cxn, sx * i2, fmaf(rc.cyn, sy * i2, rc.czn * (sz * i2)));
+  uc.mk = mk;
+  uc.e0 = half ? sx : mk;
+  uc.e1 = half ? sy : zp;
+  uc.e2 = half ? sz : ang;
+  unsigned bits = 0;
+  if (want_bits) {
+    if (zp > 0.0f) bits |= 1u;
+    if (in_mask_bounds(px, py, W, H, ctr)) bits |= 2u;
+  }
+  return bits;
+}
+
+// bilinear blend, partial dot, (hi, lo) split and the unit's 6 + 6 packed columns -> TMEM
+__device__ __forceinline__ void unit_convert(const RowCtx& rc, int unit, const UnitCtx& uc, const float4 (&f)[4][2],
+                                             uint32_t a1_lane) {
+  const int half = unit & 1;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    v[4 * j + 0] = fmaf(uc.w11, f[3][j].x, fmaf(uc.w10, f[2][j].x, fmaf(uc.w01, f[1][j].x, uc.w00 * f[0][j].x)));
+    v[4 * j + 1] = fmaf(uc.w11, f[3][j].y, fmaf(uc.w10, f[2][j].y, fmaf(uc.w01, f[1][j].y, uc.w00 * f[0][j].y)));
+    v[4 * j + 2] = fmaf(uc.w11, f[3][j].z, fmaf(uc.w10, f[2][j].z, fmaf(uc.w01, f[1][j].z, uc.w00 * f[0][j].z)));
+    v[4 * j + 3] = fmaf(uc.w11, f[3][j].w, fmaf(uc.w10, f[2][j].w, fmaf(uc.w01, f[1][j].w, uc.w00 * f[0][j].w)));
+  }
+  float dot = 0.f;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float4 c = half ? rc.cur4[2 + j] : rc.cur4[j];
+    dot = fmaf(v[4 * j], c.x, fmaf(v[4 * j + 1], c.y, fmaf(v[4 * j + 2], c.z, fmaf(v[4 * j + 3], c.w, dot))));
+  }
+  uint32_t hi[kUnitCols], lo[kUnitCols];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split_pack(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+  split_pack(dot * uc.mk, uc.e0, hi[4], lo[4]);
+  split_pack(uc.e1, uc.e2, hi[5], lo[5]);
+  const uint32_t col = (uint32_t)(kUnitCols * unit);
+  st_x4(a1_lane + col, hi);
+  st_x2(a1_lane + col + 4, hi + 4);
+  st_x4(a1_lane + kA1LoOff + col, lo);
+  st_x2(a1_lane + kA1LoOff + col + 4, lo + 4);
+}
+
 // Optional per-tile timeline of CTA 0 (experiment builds only, -DSRCV_TC_TIMELINE): one lane of
 // each role stamps %globaltimer-free SM clocks at its phase boundaries; read back with
 // srcv_debug_read_timeline.  Not compiled into the shipped library.
@@ -517,6 +656,38 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
       make_row<PER_PIXEL>(tile_id(it), row, W, H, HW, D, nd, tiles_x, tiles_xy, ctr, cur4g, frames, planes, rc);
       const bool wb = masks && rc.last_plane;
       const uint32_t a1_lane = lane_base + kColA1 + buf * kA1Stride;
+#ifdef SRCV_TC_HALF_UNITS
+      // Units 5 slot .. 5 slot + 4 (slot 2: four units and the tail), software-pipelined: the eight
+      // gathers of unit i + 1 are in flight while unit i is blended, split and stored.
+      const int u0 = 5 * slot;
+      float4 fa[4][2], fb[4][2];
+      UnitCtx ua, ub;
+#define SRCV_ISSUE(u, uc, f) bits |= unit_issue<TW, HWC>(rc, (u), src4, views, W, H, HW, ctr, wb, uc, f)
+      unsigned bits = 0;
+      SRCV_ISSUE(u0, ua, fa);
+      SRCV_ISSUE(u0 + 1, ub, fb);
+      SRCV_TL(it, 1);
+      if (use > 0) {
+        mbar_wait(bar_d2_free + buf, (use - 1) & 1u);    // tile it - 2 is completely out of this buffer
+        fence_after_sync();
+      }
+      SRCV_TL(it, 2);
+      unit_convert(rc, u0, ua, fa, a1_lane);
+      SRCV_ISSUE(u0 + 2, ua, fa);
+      unit_convert(rc, u0 + 1, ub, fb, a1_lane);
+      SRCV_ISSUE(u0 + 3, ub, fb);
+      unit_convert(rc, u0 + 2, ua, fa, a1_lane);
+      if (slot < 2) {
+        SRCV_ISSUE(u0 + 4, ua, fa);
+        unit_convert(rc, u0 + 3, ub, fb, a1_lane);
+        unit_convert(rc, u0 + 4, ua, fa, a1_lane);
+      } else {
+        unit_convert(rc, u0 + 3, ub, fb, a1_lane);
+        tail_block(rc, hi, lo);
+        store_block(a1_lane, (uint32_t)(kBlkCols * kViews), hi, lo);
+      }
+#undef SRCV_ISSUE
+#else
       unsigned bits = build_block<TW, HWC>(rc, blk_first, src4, views, W, H, HW, ctr, wb, hi, lo);
       SRCV_TL(it, 1);
       if (use > 0) {
@@ -536,6 +707,7 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
           store_block(a1_lane, (uint32_t)(kBlkCols * (blk_first + j)), hi, lo);
         }
       }
+#endif
       // Mask bits of this tile live with its buffer: the epilogue warp reads them before its
       // bar_d2_free arrival for this tile, and the next store into the slot (tile it + 2) follows
       // this thread's wait on exactly that barrier phase.
@@ -575,21 +747,21 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
         last_plane = (d == D - 1);
       }
       const float4* pb4 = reinterpret_cast<const float4*>(frame_bias + (size_t)b * kN);
-      // 64 columns per step: two TMEM loads in flight per wait, twice the independent work per
-      // dependent chain (this stage is a single warp per scheduler on the tensor pipe's critical path)
+      // kEpiStep columns per step (64: two TMEM loads in flight per wait, twice the independent
+      // work per dependent chain; 32 where the register budget of this group is 96)
 #pragma unroll 1
-      for (int c = 0; c < kN; c += 64) {
-        if (kSplitHalves || c == 0) {
+      for (int c = 0; c < kN; c += kEpiStep) {
+        if ((c & 63) == 0 && (kSplitHalves || c == 0)) {
           mbar_wait(bar_mma1 + (c >> 6), par);   // this column half of D1 is complete
           fence_after_sync();
           SRCV_TL(it, c ? 14 : 4);
         }
-        uint32_t r[64];
-        ld_x32(lane_base + kColDA + c, r);
-        ld_x32(lane_base + kColDA + c + 32, r + 32);
+        uint32_t r[kEpiStep];
+#pragma unroll
+        for (int h = 0; h < kEpiStep / 32; ++h) ld_x32(lane_base + kColDA + c + 32 * h, r + 32 * h);
         wait_ld();
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < kEpiStep / 32; ++h) {
           uint32_t ehi[16], elo[16];
 #pragma unroll
           for (int j = 0; j < 16; j += 2) {
@@ -601,11 +773,11 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
           st_x16(lane_base + kColDA + c + 32 * h, ehi);
           st_x16(lane_base + kColDA + c + 32 * h + 16, elo);
         }
-        if (kSplitHalves || c == kN - 64) {
+        if (((c + kEpiStep) & 63) == 0 && (kSplitHalves || c + kEpiStep == kN)) {
           wait_st();
           fence_before_sync();
           mbar_arrive(bar_a2_full + (c >> 6));   // k-steps 4 (c / 64) .. + 3 of the layer-2 operand
-          SRCV_TL(it, c ? 5 : 13);
+          SRCV_TL(it, (c >> 6) ? 5 : 13);
         }
       }
       // mask bits of the builders: visible since the bar_mma1 waits above (a1_full -> MMA -> commit)
@@ -621,18 +793,18 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
       const uint32_t d2_lane = lane_base + kColA1 + buf * kA1Stride;
       float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < kN; c += 64) {
-        uint32_t r[64];
-        ld_x32(d2_lane + c, r);
-        ld_x32(d2_lane + c + 32, r + 32);
+      for (int c = 0; c < kN; c += kEpiStep) {
+        uint32_t r[kEpiStep];
+#pragma unroll
+        for (int h = 0; h < kEpiStep / 32; ++h) ld_x32(d2_lane + c + 32 * h, r + 32 * h);
         wait_ld();
-        if (c == kN - 64) {
+        if (c == kN - kEpiStep) {
           fence_before_sync();
           mbar_arrive(bar_d2_free + buf);   // the buffer is free: the builders may write tile it + 2 into it
           SRCV_TL(it, 7);
         }
 #pragma unroll
-        for (int j = 0; j < 64; j += 4) {
+        for (int j = 0; j < kEpiStep; j += 4) {
           const float4 bb = *reinterpret_cast<const float4*>(svec + c + j);
           const float4 wa = *reinterpret_cast<const float4*>(svec + kN + c + j);
           const float4 wn = *reinterpret_cast<const float4*>(svec + 2 * kN + c + j);

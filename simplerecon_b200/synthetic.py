@@ -234,3 +234,27 @@ def make_mvs_scene(seed: int = 0, frames: int = 8, height: int = 96, width: int 
     images = torch.randint(0, 256, (frames, height, width, 3), generator=g, dtype=torch.uint8)
     return dict(depths=torch.stack(depths), cam_T_world=torch.stack(Ps), K=K.float().repeat(frames, 1, 1),
                 images=images)
+
+
+def make_mvloss_batch(seed: int = 0, batch: int = 2, views: int = 3, height: int = 48, width: int = 64,
+                      pred_noise: float = 0.05) -> dict:
+    """Inputs of the multi-view depth regression loss (reference losses.py:180-190, called from
+    experiment_modules/depth_model.py:477-485): per batch item a reference frame with its ground-truth
+    depth and `views` source frames of the same synthetic room scan, 4x4 intrinsics / poses, and a
+    predicted depth = ground truth x exp(noise) (positive, as the model's exp head produces)."""
+    g = torch.Generator().manual_seed(4242 + seed)
+    cur_d, src_d, invK, srcK, wTc, scTw, pred = [], [], [], [], [], [], []
+    for b in range(batch):
+        sc = make_mvs_scene(seed=seed * 131 + b, frames=views + 1, height=height, width=width)
+        K4 = torch.eye(4).repeat(views + 1, 1, 1)
+        K4[:, :3, :3] = sc["K"]
+        cur_d.append(sc["depths"][0][None])
+        src_d.append(sc["depths"][1:][:, None])
+        invK.append(torch.inverse(K4[0]))
+        srcK.append(K4[1:])
+        wTc.append(torch.inverse(sc["cam_T_world"][0]))
+        scTw.append(sc["cam_T_world"][1:])
+        pred.append((sc["depths"][0].clamp_min(0.05) * torch.exp(pred_noise * torch.randn(height, width, generator=g)))[None])
+    return dict(depth_pred_b1hw=torch.stack(pred), cur_depth_b1hw=torch.stack(cur_d), src_depth_bk1hw=torch.stack(src_d),
+                cur_invK_b44=torch.stack(invK), src_K_bk44=torch.stack(srcK), cur_world_T_cam_b44=torch.stack(wTc),
+                src_cam_T_world_bk44=torch.stack(scTw))

@@ -112,6 +112,7 @@ template <int N> inline void ld_n(uint32_t taddr, uint32_t* r) {
   for (int j = 0; j < N; ++j) r[j] = c[j];
 }
 inline void st_x1(uint32_t taddr, uint32_t r0) { st_n<1>(taddr, &r0); }
+inline void st_x2(uint32_t taddr, const uint32_t* r) { st_n<2>(taddr, r); }
 inline void st_x4(uint32_t taddr, const uint32_t* r) { st_n<4>(taddr, r); }
 inline void st_x8(uint32_t taddr, const uint32_t* r) { st_n<8>(taddr, r); }
 inline void st_x16(uint32_t taddr, const uint32_t* r) { st_n<16>(taddr, r); }
