@@ -192,8 +192,8 @@ tc_pack_kernel(srcv_mlp_weights w, uint8_t* __restrict__ image) {
   }
 }
 
-// pb[b][n] = 16 * sum_k ( W1[n, comb_k] comb(b,k) + W1[n, r_k] r(b,k) + W1[n, t_k] t(b,k) ): the
-// layer-1 contribution of the 21 pose measures, fp64 accumulation, added by the layer-1 epilogue.
+// pb[b][n] = 16 * ( b1[n] + sum_k ( W1[n, comb_k] comb(b,k) + W1[n, r_k] r(b,k) + W1[n, t_k] t(b,k) ) ): the
+// layer-1 bias of frame b = b1 + the contribution of the 21 pose measures, fp64 accumulation.
 __global__ void __launch_bounds__(kN)
 tc_frame_bias_kernel(srcv_mlp_weights w, const ViewParams* __restrict__ views, float* __restrict__ pb) {
   const int b = blockIdx.x, n = threadIdx.x;
@@ -204,7 +204,9 @@ tc_frame_bias_kernel(srcv_mlp_weights w, const ViewParams* __restrict__ views, f
     acc += (double)w.w1[(size_t)n * kF + pose_channel(1, k)] * (double)vp.rmeas;
     acc += (double)w.w1[(size_t)n * kF + pose_channel(2, k)] * (double)vp.tmeas;
   }
-  pb[(size_t)b * kN + n] = (float)((double)kWScale * acc);
+  // + b1: the MMA issuer writes this vector, split into fp16 (hi, lo), into W1's bias row whenever its
+  // CTA moves on to another frame, so the whole layer-1 bias rides in the MMA (constant-one K position)
+  pb[(size_t)b * kN + n] = (float)((double)kWScale * (acc + (double)w.b1[n]));
 }
 
 // 12 packed columns of one K block -> TMEM (hi and lo regions of the tile's A1 buffer)
@@ -284,7 +286,9 @@ __device__ __forceinline__ unsigned view_block(const RowCtx& rc, const ViewParam
   }
   // features are sampled even for points behind the camera (only the dot is masked,
   // reference modules/cost_volume.py:590-623)
-  float v[kC];
+  // blend and dot on packed pairs (FFMA2 / FMUL2: two IEEE fp32 operations per issue slot — the
+  // builders are issue-bound, not FMA-pipe-bound)
+  float2 v2[kC / 2];
   {
     const float4 *q0 = view4 + o00, *q1 = view4 + o01, *q2 = view4 + o10, *q3 = view4 + o11;
     float4 f[4][4];
@@ -295,19 +299,23 @@ __device__ __forceinline__ unsigned view_block(const RowCtx& rc, const ViewParam
       f[2][j] = __ldg(q2 + (size_t)j * HW);
       f[3][j] = __ldg(q3 + (size_t)j * HW);
     }
+    const float2 p00 = make_float2(w00, w00), p01 = make_float2(w01, w01), p10 = make_float2(w10, w10),
+                 p11 = make_float2(w11, w11);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      v[4 * j + 0] = fmaf(w11, f[3][j].x, fmaf(w10, f[2][j].x, fmaf(w01, f[1][j].x, w00 * f[0][j].x)));
-      v[4 * j + 1] = fmaf(w11, f[3][j].y, fmaf(w10, f[2][j].y, fmaf(w01, f[1][j].y, w00 * f[0][j].y)));
-      v[4 * j + 2] = fmaf(w11, f[3][j].z, fmaf(w10, f[2][j].z, fmaf(w01, f[1][j].z, w00 * f[0][j].z)));
-      v[4 * j + 3] = fmaf(w11, f[3][j].w, fmaf(w10, f[2][j].w, fmaf(w01, f[1][j].w, w00 * f[0][j].w)));
+      v2[2 * j] = fma2(p11, make_float2(f[3][j].x, f[3][j].y), fma2(p10, make_float2(f[2][j].x, f[2][j].y),
+                  fma2(p01, make_float2(f[1][j].x, f[1][j].y), mul2(p00, make_float2(f[0][j].x, f[0][j].y)))));
+      v2[2 * j + 1] = fma2(p11, make_float2(f[3][j].z, f[3][j].w), fma2(p10, make_float2(f[2][j].z, f[2][j].w),
+                      fma2(p01, make_float2(f[1][j].z, f[1][j].w), mul2(p00, make_float2(f[0][j].z, f[0][j].w)))));
     }
   }
-  float dot = 0.f;
+  float2 d2 = make_float2(0.f, 0.f);       // even / odd channel partial sums
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
-    dot = fmaf(v[4 * j], rc.cur4[j].x, fmaf(v[4 * j + 1], rc.cur4[j].y,
-          fmaf(v[4 * j + 2], rc.cur4[j].z, fmaf(v[4 * j + 3], rc.cur4[j].w, dot))));
+  for (int j = 0; j < 4; ++j) {
+    d2 = fma2(v2[2 * j], make_float2(rc.cur4[j].x, rc.cur4[j].y), d2);
+    d2 = fma2(v2[2 * j + 1], make_float2(rc.cur4[j].z, rc.cur4[j].w), d2);
+  }
+  const float dot = d2.x + d2.y;
   const float mk = zp > 0.0f ? 1.0f : 0.0f;
   // n_src = (X - centre_k)/max(|.|, 1e-12) ; ray angle = cosine_similarity(n_cur, n_src, eps 1e-5)
   const float sx0 = rc.X - vr.centre[0], sy0 = rc.Y - vr.centre[1], sz0 = rc.Z - vr.centre[2];
@@ -316,7 +324,7 @@ __device__ __forceinline__ unsigned view_block(const RowCtx& rc, const ViewParam
   const float i2 = inv_norm(fmaf(sx, sx, fmaf(sy, sy, sz * sz)), kEpsCos);
   const float ang = fmaf(rc.cxn, sx * i2, fmaf(rc.cyn, sy * i2, rc.czn * (sz * i2)));
 #pragma unroll
-  for (int i = 0; i < 8; ++i) split_pack(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+  for (int i = 0; i < 8; ++i) split_pack(v2[i].x, v2[i].y, hi[i], lo[i]);
   split_pack(mk, zp, hi[8], lo[8]);
   split_pack(dot * mk, ang, hi[9], lo[9]);
   split_pack(sx, sy, hi[10], lo[10]);
@@ -746,7 +754,6 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
         out = active ? ((long long)b * D + d) * HW + ((y0 + ry) * W + (x0 + rx)) : -1;
         last_plane = (d == D - 1);
       }
-      const float4* pb4 = reinterpret_cast<const float4*>(frame_bias + (size_t)b * kN);
       // kEpiStep columns per step (64: two TMEM loads in flight per wait, twice the independent
       // work per dependent chain; 32 where the register budget of this group is 96)
 #pragma unroll 1
@@ -764,11 +771,12 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
         for (int h = 0; h < kEpiStep / 32; ++h) {
           uint32_t ehi[16], elo[16];
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            const float4 pb = __ldg(pb4 + (c + 32 * h + 2 * j) / 4);   // per-frame pose bias (x16, like the accumulator)
-            const uint32_t* q = r + 32 * h + 2 * j;
-            split_pack(leaky(__uint_as_float(q[0]) + pb.x), leaky(__uint_as_float(q[1]) + pb.y), ehi[j], elo[j]);
-            split_pack(leaky(__uint_as_float(q[2]) + pb.z), leaky(__uint_as_float(q[3]) + pb.w), ehi[j + 1], elo[j + 1]);
+          for (int j = 0; j < 16; ++j) {
+            // LeakyReLU = max(x, 0.01 x), the multiply as one packed FMUL2 per column pair (the
+            // bias, incl. the frame's pose measures, came out of the MMA)
+            const float2 x = make_float2(__uint_as_float(r[32 * h + 2 * j]), __uint_as_float(r[32 * h + 2 * j + 1]));
+            const float2 m = mul2(x, make_float2(kLeaky, kLeaky));
+            split_pack(fmaxf(x.x, m.x), fmaxf(x.y, m.y), ehi[j], elo[j]);
           }
           st_x16(lane_base + kColDA + c + 32 * h, ehi);
           st_x16(lane_base + kColDA + c + 32 * h + 16, elo);
@@ -791,7 +799,7 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
       fence_after_sync();
       SRCV_TL(it, 6);
       const uint32_t d2_lane = lane_base + kColA1 + buf * kA1Stride;
-      float acc0 = 0.f, acc1 = 0.f;
+      float2 acc2 = make_float2(0.f, 0.f);     // even / odd columns, as packed FFMA2 chains
 #pragma unroll 1
       for (int c = 0; c < kN; c += kEpiStep) {
         uint32_t r[kEpiStep];
@@ -808,18 +816,15 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
           const float4 bb = *reinterpret_cast<const float4*>(svec + c + j);
           const float4 wa = *reinterpret_cast<const float4*>(svec + kN + c + j);
           const float4 wn = *reinterpret_cast<const float4*>(svec + 2 * kN + c + j);
-          const float h0 = fmaf(__uint_as_float(r[j + 0]), kUnscale2, bb.x);
-          const float h1 = fmaf(__uint_as_float(r[j + 1]), kUnscale2, bb.y);
-          const float h2 = fmaf(__uint_as_float(r[j + 2]), kUnscale2, bb.z);
-          const float h3 = fmaf(__uint_as_float(r[j + 3]), kUnscale2, bb.w);
-          acc0 = fmaf(wn.x, fabsf(h0), fmaf(wa.x, h0, acc0));
-          acc1 = fmaf(wn.y, fabsf(h1), fmaf(wa.y, h1, acc1));
-          acc0 = fmaf(wn.z, fabsf(h2), fmaf(wa.z, h2, acc0));
-          acc1 = fmaf(wn.w, fabsf(h3), fmaf(wa.w, h3, acc1));
+          const float2 us = make_float2(kUnscale2, kUnscale2);
+          const float2 h01 = fma2(make_float2(__uint_as_float(r[j + 0]), __uint_as_float(r[j + 1])), us, make_float2(bb.x, bb.y));
+          const float2 h23 = fma2(make_float2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), us, make_float2(bb.z, bb.w));
+          acc2 = fma2(make_float2(wn.x, wn.y), make_float2(fabsf(h01.x), fabsf(h01.y)), fma2(make_float2(wa.x, wa.y), h01, acc2));
+          acc2 = fma2(make_float2(wn.z, wn.w), make_float2(fabsf(h23.x), fabsf(h23.y)), fma2(make_float2(wa.z, wa.w), h23, acc2));
         }
       }
       if (out >= 0) {
-        cost[out] = (acc0 + acc1) + svec[3 * kN];
+        cost[out] = (acc2.x + acc2.y) + svec[3 * kN];
         if (masks && last_plane) {
           // overall mask of the LAST plane (reference :625-637): any view in front AND any view
           // inside the 2-pixel border, independently
@@ -835,9 +840,30 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
     if (warp == kMmaWarp) {
       // =============================== MMA issuer ==========================================
       const uint32_t sbase = smem_u32(smem);
+      __half* w1hi = reinterpret_cast<__half*>(smem + kOffW1Hi);
+      __half* w1lo = reinterpret_cast<__half*>(smem + kOffW1Lo);
+      int bias_frame = -1;
       for (unsigned it = 0; it < n_local; ++it) {
         const uint32_t par = it & 1u, buf = it & 1u, use = it >> 1;
         const uint32_t a1 = tmem_base + kColA1 + buf * kA1Stride;
+        // The layer-1 bias of the tile's frame (b1 + its pose measures) is W1's row at the constant-one
+        // K position: rewritten (fp16 hi, lo) when the CTA's tiles move on to another frame.  Its
+        // readers — the layer-1 MMAs of earlier tiles — completed before this warp issued the
+        // previous tile's last layer-2 MMAs (bar_mma1 -> epilogue -> bar_a2_full -> here).
+        const int fb = (int)(tile_id(it) / (nd * tiles_xy));
+        if (fb != bias_frame) {
+          bias_frame = fb;
+#pragma unroll
+          for (int i = 0; i < kN / 32; ++i) {
+            const int n = lane + 32 * i;
+            const float v = __ldg(frame_bias + (size_t)fb * kN + n);
+            const __half h = __float2half_rn(v);
+            w1hi[core_offset(n, kBiasPos, kN)] = h;
+            w1lo[core_offset(n, kBiasPos, kN)] = __float2half_rn(v - __half2float(h));
+          }
+          fence_proxy_async_smem();                // generic-proxy stores -> visible to the tensor core
+          __syncwarp();
+        }
         mbar_wait(bar_a1_full + buf, use & 1u);   // A1 of this tile is in TMEM
         fence_after_sync();
         SRCV_TL(it, 9);
