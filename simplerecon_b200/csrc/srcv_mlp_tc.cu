@@ -81,18 +81,12 @@ constexpr int kBuildWarps = 12, kEpiWarps = 4, kMmaWarp = 16;
 constexpr int kThreads = 20 * 32;
 constexpr int kBuilders = kBuildWarps * 32, kEpis = kEpiWarps * 32;
 constexpr int kRegsLaunch = 96;          // what ptxas allocates under __launch_bounds__(640, 1)
-#ifdef SRCV_TC_HALF_UNITS
-// Half-view units (below): a builder thread keeps the eight gathers of the NEXT unit in flight while
-// it converts the current one — two 32-register gather buffers — so the builders take 120 registers
-// and the epilogue warps work in 32-column steps within 96.
-constexpr bool kHalfUnits = true;
-constexpr int kRegsBuild = 120, kRegsEpi = 96, kRegsMma = 24;
-constexpr int kEpiStep = 32;
-#else
-constexpr bool kHalfUnits = false;
 constexpr int kRegsBuild = 112, kRegsEpi = 120, kRegsMma = 24;
 constexpr int kEpiStep = 64;
-#endif
+// The 7 view blocks + the tail do not divide by the three builder threads of a row: view kSplitView is
+// built as TWO half-view units (channels 8h..8h+7 each, see unit_issue) by slots 0 and 1, so the slots
+// carry 2.5 / 2.5 / 2 views + tail instead of 3 / 3 / 1 + tail.
+constexpr int kSplitView = 2;
 static_assert(kBuilders * kRegsBuild + kEpis * kRegsEpi + (kThreads - kBuilders - kEpis) * kRegsMma <= kThreads * kRegsLaunch,
               "setmaxnreg budget: increases must be covered by the decreases within the CTA's launch allocation");
 static_assert(kRegsBuild % 8 == 0 && kRegsEpi % 8 == 0 && kRegsMma % 8 == 0, "setmaxnreg takes multiples of 8");
@@ -118,8 +112,8 @@ __host__ __device__ inline uint32_t core_offset(int n, int k, int N) {
 // view) are NOT in K: they are constant per (frame, view), so their layer-1 contribution is a
 // per-frame bias vector (tc_frame_bias_kernel) added in the layer-1 epilogue.
 __host__ __device__ inline int ref_channel(int kk) {
-  if (kHalfUnits && kk < kViews * kBlk) {
-    // half-view units: a view block is two units of 12 K positions, unit h of view k =
+  if (kk / kBlk == kSplitView) {
+    // the split view's block is two units of 12 K positions, unit h =
     //   8 warped features (channels 8h..8h+7) | partial dot over those channels | three measures:
     //   h = 0: mask, z', ray angle      h = 1: n_src (3)
     // The dot appears twice (both partial sums meet the same W1 column; the MMA adds them).
@@ -350,14 +344,12 @@ __device__ __forceinline__ void tail_block(const RowCtx& rc, uint32_t (&hi)[kBlk
   hi[11] = 0u; lo[11] = 0u;
 }
 
-// ---- half-view units (-DSRCV_TC_HALF_UNITS) ---------------------------------------------------
+// ---- half-view unit: how view kSplitView is built ------------------------------------------------
 // A unit = one source view, channels 8h..8h+7: eight vector gathers, eight warped channels, the
 // partial dot over those channels and three of the view's six per-sample measures = 6 packed
-// columns.  The 14 units + the tail spread 5 / 5 / 4+tail over the three threads of a row (the
-// whole-view split was 3 / 3 / 1+tail views: the builders' critical path drops from 3 to 2.5 views),
-// and a unit is small enough to keep the NEXT unit's gathers in flight while this one is converted.
+// columns.  The projection is done by both threads that share the view (~70 instructions each);
+// what moves off the critical slots is half of the gathers, the blend, the split and the stores.
 constexpr int kUnitCols = kBlkCols / 2;     // 6
-constexpr int kUnits = 2 * kViews;          // 14; unit index 14 = the tail block
 
 // what the conversion of a unit needs once its gathers are under way
 struct UnitCtx {
@@ -367,11 +359,10 @@ struct UnitCtx {
 
 // project, set the footprint up and ISSUE the unit's eight gathers (f: [tap][chunk of the half])
 template <int TW, int HWC>
-__device__ __forceinline__ unsigned unit_issue(const RowCtx& rc, int unit, const float4* __restrict__ src4,
+__device__ __forceinline__ unsigned unit_issue(const RowCtx& rc, int k, int half, const float4* __restrict__ src4,
                                                const ViewParams* __restrict__ views, int Wrt, int H, int HWrt,
                                                const Centre& ctr, bool want_bits, UnitCtx& uc, float4 (&f)[4][2]) {
   const int W = TW ? TW : Wrt, HW = HWC ? HWC : HWrt;
-  const int k = unit >> 1, half = unit & 1;
   const ViewParams* vpp = views + (rc.b * kViews + k);
   const float4* view4 = src4 + ((size_t)(rc.b * kViews + k) * 4 + 2 * half) * HW;
   ViewRegs vr;
@@ -437,29 +428,27 @@ __device__ __forceinline__ unsigned unit_issue(const RowCtx& rc, int unit, const
 }
 
 // bilinear blend, partial dot, (hi, lo) split and the unit's 6 + 6 packed columns -> TMEM
-__device__ __forceinline__ void unit_convert(const RowCtx& rc, int unit, const UnitCtx& uc, const float4 (&f)[4][2],
-                                             uint32_t a1_lane) {
-  const int half = unit & 1;
-  float v[8];
+__device__ __forceinline__ void unit_convert(const RowCtx& rc, int k, int half, const UnitCtx& uc,
+                                             const float4 (&f)[4][2], uint32_t a1_lane) {
+  const float2 p00 = make_float2(uc.w00, uc.w00), p01 = make_float2(uc.w01, uc.w01),
+               p10 = make_float2(uc.w10, uc.w10), p11 = make_float2(uc.w11, uc.w11);
+  float2 v2[4], d2 = make_float2(0.f, 0.f);
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
-    v[4 * j + 0] = fmaf(uc.w11, f[3][j].x, fmaf(uc.w10, f[2][j].x, fmaf(uc.w01, f[1][j].x, uc.w00 * f[0][j].x)));
-    v[4 * j + 1] = fmaf(uc.w11, f[3][j].y, fmaf(uc.w10, f[2][j].y, fmaf(uc.w01, f[1][j].y, uc.w00 * f[0][j].y)));
-    v[4 * j + 2] = fmaf(uc.w11, f[3][j].z, fmaf(uc.w10, f[2][j].z, fmaf(uc.w01, f[1][j].z, uc.w00 * f[0][j].z)));
-    v[4 * j + 3] = fmaf(uc.w11, f[3][j].w, fmaf(uc.w10, f[2][j].w, fmaf(uc.w01, f[1][j].w, uc.w00 * f[0][j].w)));
-  }
-  float dot = 0.f;
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
+    v2[2 * j] = fma2(p11, make_float2(f[3][j].x, f[3][j].y), fma2(p10, make_float2(f[2][j].x, f[2][j].y),
+                fma2(p01, make_float2(f[1][j].x, f[1][j].y), mul2(p00, make_float2(f[0][j].x, f[0][j].y)))));
+    v2[2 * j + 1] = fma2(p11, make_float2(f[3][j].z, f[3][j].w), fma2(p10, make_float2(f[2][j].z, f[2][j].w),
+                    fma2(p01, make_float2(f[1][j].z, f[1][j].w), mul2(p00, make_float2(f[0][j].z, f[0][j].w)))));
     const float4 c = half ? rc.cur4[2 + j] : rc.cur4[j];
-    dot = fmaf(v[4 * j], c.x, fmaf(v[4 * j + 1], c.y, fmaf(v[4 * j + 2], c.z, fmaf(v[4 * j + 3], c.w, dot))));
+    d2 = fma2(v2[2 * j], make_float2(c.x, c.y), d2);
+    d2 = fma2(v2[2 * j + 1], make_float2(c.z, c.w), d2);
   }
   uint32_t hi[kUnitCols], lo[kUnitCols];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) split_pack(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
-  split_pack(dot * uc.mk, uc.e0, hi[4], lo[4]);
+  for (int i = 0; i < 4; ++i) split_pack(v2[i].x, v2[i].y, hi[i], lo[i]);
+  split_pack((d2.x + d2.y) * uc.mk, uc.e0, hi[4], lo[4]);
   split_pack(uc.e1, uc.e2, hi[5], lo[5]);
-  const uint32_t col = (uint32_t)(kUnitCols * unit);
+  const uint32_t col = (uint32_t)(kBlkCols * k + kUnitCols * half);
   st_x4(a1_lane + col, hi);
   st_x2(a1_lane + col + 4, hi + 4);
   st_x4(a1_lane + kA1LoOff + col, lo);
@@ -645,8 +634,8 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
 
   if (warp < kBuildWarps) {
     // =============================== builders ============================================
-    // Twelve warps: three threads per row (slot = warp / 4), each building a contiguous range of
-    // K blocks — slots 0 and 1 three source views each, slot 2 the last view and the tail.  With
+    // Twelve warps: three threads per row (slot = warp / 4): two whole source views each, then half of
+    // view kSplitView (slots 0, 1) or the tail (slot 2).  With
     // two A1 buffers they run up to a whole tile ahead of the tensor pipe: buffer t & 1 is free
     // again once the layer-2 epilogue of tile t - 2 has read its accumulator out of it.
 #ifndef SRCV_TC_NO_SETMAXNREG
@@ -654,7 +643,9 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
 #endif
     const int row = (warp & 3) * 32 + lane, slot = warp >> 2;
     const Centre ctr(W, H);
-    const int blk_first = 3 * slot, blk_count = (slot < 2) ? 3 : 2;
+    // slot 0: views 0, 1 + the first half of view kSplitView; slot 1: views 3, 4 + its second half;
+    // slot 2: views 5, 6 + the tail
+    const int blk_first = (slot < 2) ? 3 * slot : 5;
     const bool masks = mask_out != nullptr;
     RowCtx rc;
     uint32_t hi[kBlkCols], lo[kBlkCols];
@@ -664,38 +655,6 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
       make_row<PER_PIXEL>(tile_id(it), row, W, H, HW, D, nd, tiles_x, tiles_xy, ctr, cur4g, frames, planes, rc);
       const bool wb = masks && rc.last_plane;
       const uint32_t a1_lane = lane_base + kColA1 + buf * kA1Stride;
-#ifdef SRCV_TC_HALF_UNITS
-      // Units 5 slot .. 5 slot + 4 (slot 2: four units and the tail), software-pipelined: the eight
-      // gathers of unit i + 1 are in flight while unit i is blended, split and stored.
-      const int u0 = 5 * slot;
-      float4 fa[4][2], fb[4][2];
-      UnitCtx ua, ub;
-#define SRCV_ISSUE(u, uc, f) bits |= unit_issue<TW, HWC>(rc, (u), src4, views, W, H, HW, ctr, wb, uc, f)
-      unsigned bits = 0;
-      SRCV_ISSUE(u0, ua, fa);
-      SRCV_ISSUE(u0 + 1, ub, fb);
-      SRCV_TL(it, 1);
-      if (use > 0) {
-        mbar_wait(bar_d2_free + buf, (use - 1) & 1u);    // tile it - 2 is completely out of this buffer
-        fence_after_sync();
-      }
-      SRCV_TL(it, 2);
-      unit_convert(rc, u0, ua, fa, a1_lane);
-      SRCV_ISSUE(u0 + 2, ua, fa);
-      unit_convert(rc, u0 + 1, ub, fb, a1_lane);
-      SRCV_ISSUE(u0 + 3, ub, fb);
-      unit_convert(rc, u0 + 2, ua, fa, a1_lane);
-      if (slot < 2) {
-        SRCV_ISSUE(u0 + 4, ua, fa);
-        unit_convert(rc, u0 + 3, ub, fb, a1_lane);
-        unit_convert(rc, u0 + 4, ua, fa, a1_lane);
-      } else {
-        unit_convert(rc, u0 + 3, ub, fb, a1_lane);
-        tail_block(rc, hi, lo);
-        store_block(a1_lane, (uint32_t)(kBlkCols * kViews), hi, lo);
-      }
-#undef SRCV_ISSUE
-#else
       unsigned bits = build_block<TW, HWC>(rc, blk_first, src4, views, W, H, HW, ctr, wb, hi, lo);
       SRCV_TL(it, 1);
       if (use > 0) {
@@ -704,18 +663,17 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
       }
       SRCV_TL(it, 2);
       store_block(a1_lane, (uint32_t)(kBlkCols * blk_first), hi, lo);
-#ifdef SRCV_TC_UNROLL_BLOCKS
-#pragma unroll
-#else
-#pragma unroll 1
-#endif
-      for (int j = 1; j < 3; ++j) {
-        if (j < blk_count) {
-          bits |= build_block<TW, HWC>(rc, blk_first + j, src4, views, W, H, HW, ctr, wb, hi, lo);
-          store_block(a1_lane, (uint32_t)(kBlkCols * (blk_first + j)), hi, lo);
-        }
+      bits |= build_block<TW, HWC>(rc, blk_first + 1, src4, views, W, H, HW, ctr, wb, hi, lo);
+      store_block(a1_lane, (uint32_t)(kBlkCols * (blk_first + 1)), hi, lo);
+      if (slot < 2) {
+        float4 f[4][2];
+        UnitCtx uc;
+        bits |= unit_issue<TW, HWC>(rc, kSplitView, slot, src4, views, W, H, HW, ctr, wb, uc, f);
+        unit_convert(rc, kSplitView, slot, uc, f, a1_lane);
+      } else {
+        tail_block(rc, hi, lo);
+        store_block(a1_lane, (uint32_t)(kBlkCols * kViews), hi, lo);
       }
-#endif
       // Mask bits of this tile live with its buffer: the epilogue warp reads them before its
       // bar_d2_free arrival for this tile, and the next store into the slot (tile it + 2) follows
       // this thread's wait on exactly that barrier phase.
