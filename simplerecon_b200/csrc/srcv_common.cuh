@@ -45,6 +45,34 @@ constexpr float kEpsNorm = 1e-12f;  // F.normalize default
 constexpr float kEpsCos = 1e-5f;    // modules/cost_volume.py:687
 constexpr float kLeaky = 0.01f;     // nn.LeakyReLU default slope
 
+// ---- packed fp32: two independent IEEE FMAs / multiplies in ONE issue slot (SASS FFMA2 / FMUL2) ----
+// Bit-identical to the two scalar operations; what they save is issue bandwidth, which is what the
+// sweeps' gather / blend loops and the epilogue warps of the tcgen05 kernel are short of.
+#ifdef SRCV_HOST_EMU
+inline float2 fma2(float2 a, float2 b, float2 c) { return float2{std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)}; }
+inline float2 mul2(float2 a, float2 b) { return float2{a.x * b.x, a.y * b.y}; }
+#else
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+#endif
+
 // Per (frame b, view k) constants, written by prep_kernel.  32 floats = 128 B.
 struct __align__(16) ViewParams {
   float a0[3];     // centred homography applied to the image centre

@@ -205,29 +205,6 @@ template <int N> __device__ __forceinline__ void reg_dec() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
-// ---- packed fp32: two independent IEEE FMAs / multiplies in ONE issue slot (SASS FFMA2 / FMUL2) ----
-// Bit-identical to the two scalar operations; what they save is issue bandwidth, which is what the
-// builder and epilogue warps of the sweep compete for.
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
-  unsigned long long ra, rb, rc, rd;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-  float2 d;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
-  return d;
-}
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
-  unsigned long long ra, rb, rd;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
-  float2 d;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
-  return d;
-}
-
 // ---- fp32 -> (hi, lo) fp16 pair split -------------------------------------------------------
 // x = hi + lo with hi = rn16(x), lo = rn16(x - hi): 22 significand bits survive, so
 //   A*W ~= A_hi*W_hi + A_hi*W_lo + A_lo*W_hi   (three fp16 MMAs, fp32 accumulate)

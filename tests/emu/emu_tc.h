@@ -199,8 +199,6 @@ inline uint16_t f16_sat_bits(float x) {
   std::memcpy(&b, &h, 2);
   return b;
 }
-inline float2 fma2(float2 a, float2 b, float2 c) { return float2{std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)}; }
-inline float2 mul2(float2 a, float2 b) { return float2{a.x * b.x, a.y * b.y}; }
 inline uint32_t pack_f16x2_sat(float even, float odd) {
   return (uint32_t)f16_sat_bits(even) | ((uint32_t)f16_sat_bits(odd) << 16);
 }
