@@ -77,9 +77,33 @@ constexpr float kUnscale2 = 1.0f / (kWScale * kWScale);
 // footprint in flight) and the epilogue group to 120.
 // setmaxnreg only REDISTRIBUTES the CTA's launch-time allocation (640 x 96 registers): an .inc
 // blocks until the pool holds enough, so the totals below must fit it or the CTA deadlocks.
+#ifdef SRCV_TC_W24
+// 24 warps: SIXTEEN builder warps (four threads per row, two K blocks each: views 2s, 2s+1; slot 3 the
+// last view and the tail), four epilogue warps, the MMA warp and its three idle group mates.  Registers
+// are allocated per four warps, so 768 threads launch at 80; the MMA group's 56 x 128 freed registers go
+// to the epilogue group (and, in the B split, to the builders).
+constexpr int kBuildWarps = 16, kEpiWarps = 4, kMmaWarp = 20;
+constexpr int kThreads = 24 * 32;
+constexpr int kSlots = 4;
+constexpr bool kSetmaxnreg = true;
+constexpr int kRegsLaunch = 80;
+#ifdef SRCV_TC_W24B
+constexpr int kRegsBuild = 88, kRegsEpi = 104, kRegsMma = 24;
+constexpr int kEpiStep = 32;
+#else
+constexpr int kRegsBuild = 80, kRegsEpi = 120, kRegsMma = 24;
+constexpr int kEpiStep = 64;
+#endif
+constexpr int kSplitView = -1;           // no view is split: 2 / 2 / 2 / 1 + tail blocks per slot
+#else
 constexpr int kBuildWarps = 12, kEpiWarps = 4, kMmaWarp = 16;
 constexpr int kThreads = 20 * 32;
-constexpr int kBuilders = kBuildWarps * 32, kEpis = kEpiWarps * 32;
+constexpr int kSlots = 3;
+#ifdef SRCV_TC_NO_SETMAXNREG
+constexpr bool kSetmaxnreg = false;
+#else
+constexpr bool kSetmaxnreg = true;
+#endif
 constexpr int kRegsLaunch = 96;          // what ptxas allocates under __launch_bounds__(640, 1)
 constexpr int kRegsBuild = 112, kRegsEpi = 120, kRegsMma = 24;
 constexpr int kEpiStep = 64;
@@ -87,7 +111,9 @@ constexpr int kEpiStep = 64;
 // built as TWO half-view units (channels 8h..8h+7 each, see unit_issue) by slots 0 and 1, so the slots
 // carry 2.5 / 2.5 / 2 views + tail instead of 3 / 3 / 1 + tail.
 constexpr int kSplitView = 2;
-static_assert(kBuilders * kRegsBuild + kEpis * kRegsEpi + (kThreads - kBuilders - kEpis) * kRegsMma <= kThreads * kRegsLaunch,
+#endif
+constexpr int kBuilders = kBuildWarps * 32, kEpis = kEpiWarps * 32;
+static_assert(!kSetmaxnreg || kBuilders * kRegsBuild + kEpis * kRegsEpi + (kThreads - kBuilders - kEpis) * kRegsMma <= kThreads * kRegsLaunch,
               "setmaxnreg budget: increases must be covered by the decreases within the CTA's launch allocation");
 static_assert(kRegsBuild % 8 == 0 && kRegsEpi % 8 == 0 && kRegsMma % 8 == 0, "setmaxnreg takes multiples of 8");
 
@@ -98,7 +124,7 @@ constexpr uint32_t kOffW1Hi = 0, kOffW1Lo = kW1Bytes, kOffW2Hi = 2 * kW1Bytes,
 constexpr uint32_t kVecFloats = 3 * kN + 4;   // b2 | 0.505 w3 | 0.495 w3 | b3
 constexpr uint32_t kOffBar = kOffVec + kVecFloats * 4;
 constexpr uint32_t kOffFlag = kOffBar + 12 * 8;           // 12 mbarrier slots (10 used)
-constexpr uint32_t kSmemBytes = kOffFlag + 2 * 3 * kRows;   // mask bits [parity][builder slot][row]
+constexpr uint32_t kSmemBytes = kOffFlag + 2 * kSlots * kRows;   // mask bits [parity][builder slot][row]
 // image = [W1hi | W1lo | W2hi | W2lo | vec] exactly as it sits in shared memory
 constexpr uint32_t kImageBytes = kOffBar;
 
@@ -112,7 +138,7 @@ __host__ __device__ inline uint32_t core_offset(int n, int k, int N) {
 // view) are NOT in K: they are constant per (frame, view), so their layer-1 contribution is a
 // per-frame bias vector (tc_frame_bias_kernel) added in the layer-1 epilogue.
 __host__ __device__ inline int ref_channel(int kk) {
-  if (kk / kBlk == kSplitView) {
+  if (kSplitView >= 0 && kk / kBlk == kSplitView) {
     // the split view's block is two units of 12 K positions, unit h =
     //   8 warped features (channels 8h..8h+7) | partial dot over those channels | three measures:
     //   h = 0: mask, z', ray angle      h = 1: n_src (3)
@@ -638,14 +664,12 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
     // view kSplitView (slots 0, 1) or the tail (slot 2).  With
     // two A1 buffers they run up to a whole tile ahead of the tensor pipe: buffer t & 1 is free
     // again once the layer-2 epilogue of tile t - 2 has read its accumulator out of it.
-#ifndef SRCV_TC_NO_SETMAXNREG
-    reg_inc<kRegsBuild>();
-#endif
+    if (kSetmaxnreg && kRegsBuild > kRegsLaunch) reg_inc<kRegsBuild>();
     const int row = (warp & 3) * 32 + lane, slot = warp >> 2;
     const Centre ctr(W, H);
     // slot 0: views 0, 1 + the first half of view kSplitView; slot 1: views 3, 4 + its second half;
     // slot 2: views 5, 6 + the tail
-    const int blk_first = (slot < 2) ? 3 * slot : 5;
+    const int blk_first = kSlots == 4 ? 2 * slot : ((slot < 2) ? 3 * slot : 5);
     const bool masks = mask_out != nullptr;
     RowCtx rc;
     uint32_t hi[kBlkCols], lo[kBlkCols];
@@ -663,9 +687,11 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
       }
       SRCV_TL(it, 2);
       store_block(a1_lane, (uint32_t)(kBlkCols * blk_first), hi, lo);
-      bits |= build_block<TW, HWC>(rc, blk_first + 1, src4, views, W, H, HW, ctr, wb, hi, lo);
+      bits |= build_block<TW, HWC>(rc, blk_first + 1, src4, views, W, H, HW, ctr, wb, hi, lo);   // slot 3 of 4: the tail
       store_block(a1_lane, (uint32_t)(kBlkCols * (blk_first + 1)), hi, lo);
-      if (slot < 2) {
+      if (kSlots == 4) {
+        // two blocks per thread: done
+      } else if (slot < 2) {
         float4 f[4][2];
         UnitCtx uc;
         bits |= unit_issue<TW, HWC>(rc, kSplitView, slot, src4, views, W, H, HW, ctr, wb, uc, f);
@@ -677,7 +703,7 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
       // Mask bits of this tile live with its buffer: the epilogue warp reads them before its
       // bar_d2_free arrival for this tile, and the next store into the slot (tile it + 2) follows
       // this thread's wait on exactly that barrier phase.
-      if (wb) sflag[(buf * 3 + slot) * kRows + row] = (uint8_t)bits;
+      if (wb) sflag[(buf * kSlots + slot) * kRows + row] = (uint8_t)bits;
       wait_st();
       fence_before_sync();
       mbar_arrive(bar_a1_full + buf);
@@ -689,9 +715,7 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
     // split, layer-2 operand written IN PLACE over the accumulator, 32 columns at a time (a
     // chunk's 32 fp32 columns become its 16 hi + 16 lo operand columns).  Layer-2 epilogue: bias,
     // LeakyReLU and the 128 -> 1 layer as one dot product per row — no cross-thread reduction.
-#ifndef SRCV_TC_NO_SETMAXNREG
-    reg_inc<kRegsEpi>();
-#endif
+    if (kSetmaxnreg) reg_inc<kRegsEpi>();
     const int row = (warp & 3) * 32 + lane;
     const bool masks = mask_out != nullptr;
     for (unsigned it = 0; it < n_local; ++it) {
@@ -749,8 +773,9 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
       // mask bits of the builders: visible since the bar_mma1 waits above (a1_full -> MMA -> commit)
       unsigned tile_bits = 0;
       if (masks && last_plane) {
-        const uint8_t* fl = sflag + buf * 3 * kRows + row;
-        tile_bits = fl[0] | fl[kRows] | fl[2 * kRows];
+        const uint8_t* fl = sflag + buf * kSlots * kRows + row;
+#pragma unroll
+        for (int q = 0; q < kSlots; ++q) tile_bits |= fl[q * kRows];
       }
       // ---- layer-2 epilogue: the accumulator sits in the first 128 columns of this tile's A1 buffer
       mbar_wait(bar_mma2, par);
@@ -792,9 +817,7 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
       SRCV_TL(it, 8);
     }
   } else {
-#ifndef SRCV_TC_NO_SETMAXNREG
-    reg_dec<kRegsMma>();
-#endif
+    if (kSetmaxnreg) reg_dec<kRegsMma>();
     if (warp == kMmaWarp) {
       // =============================== MMA issuer ==========================================
       const uint32_t sbase = smem_u32(smem);

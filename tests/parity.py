@@ -49,16 +49,47 @@ def load_golden(name):
     return g, inputs, sd
 
 
+def golden_fullsize_names():
+    return sorted(p.stem for p in (GOLDEN / "fullsize").glob("*.npz"))
+
+
+def load_golden_fullsize(name):
+    """Fixtures at the bench feature-map size (tests/golden/make_golden_fullsize.py): the inputs are
+    REGENERATED from the stored generator call and checked against the stored SHA-256; outputs are the
+    unmodified reference's.  Returns (g, inputs, state_dict or None) like load_golden; g["ref_cost64"]
+    is the fp64 evaluation rounded to fp32 and g["err32v64"] the reference's own max|fp32 - fp64|."""
+    import ast
+    import hashlib
+
+    from simplerecon_b200.synthetic import make_tuple, mlp_state
+    z = np.load(GOLDEN / "fullsize" / f"{name}.npz")
+    gen = dict(ast.literal_eval(str(z["gen"])))
+    inputs = make_tuple(**gen)
+    h = hashlib.sha256()
+    for k in INPUT_KEYS:
+        h.update(np.ascontiguousarray(inputs[k].numpy()).tobytes())
+    if h.hexdigest() != str(z["sha256"]):
+        raise RuntimeError(f"{name}: regenerated inputs do not hash to the stored value (generator drift)")
+    g = {k: torch.from_numpy(z[k]) for k in ("ref_cost", "ref_cost64_as_f32", "ref_lowest", "ref_planes")}
+    g["ref_cost64"] = g.pop("ref_cost64_as_f32").double()
+    g["err32v64"] = float(z["err32v64"])
+    g["kind"], g["D"] = str(z["kind"]), int(z["D"])
+    if "ref_mask" in z.files:
+        g["ref_mask"] = torch.from_numpy(z["ref_mask"])
+    sd = mlp_state(gen["views"], gen["channels"], seed=gen["seed"]) if g["kind"] == "mlp" else None
+    return g, inputs, sd
+
+
 def cost_tol(kind, ref):
     return RTOL_MAX[kind] * float(ref.abs().max()) + 1e-6
 
 
-def assert_cost_close(kind, ours, ref32, ref64=None, what=""):
+def assert_cost_close(kind, ours, ref32, ref64=None, what="", e_ref=None):
+    """`e_ref`: the reference's own max|fp32 - fp64| when `ref64` is stored rounded to fp32."""
     ours = ours.detach().cpu()
     tol = cost_tol(kind, ref32)
-    e_ref = None
     if ref64 is not None:
-        e_ref = (ref32.double() - ref64).abs().max().item()
+        e_ref = (ref32.double() - ref64).abs().max().item() if e_ref is None else e_ref
         tol = max(tol, 2 * e_ref)
     err = (ours - ref32).abs().max().item()
     assert err <= tol, f"{what}: cost max-abs err {err:.3e} > tol {tol:.3e}"

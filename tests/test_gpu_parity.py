@@ -10,7 +10,7 @@ from oracle import costvolume_oracle as O
 from simplerecon_b200 import _native
 from simplerecon_b200.synthetic import CONFIGS, make_tuple, make_workload_tuple, mlp_state, to_device
 from tests.parity import (assert_cost_close, assert_lowest_close, assert_mask_close, cost_tol,
-                          golden_names, load_golden)
+                          golden_fullsize_names, golden_names, load_golden, load_golden_fullsize)
 
 pytestmark = pytest.mark.gpu
 
@@ -76,6 +76,22 @@ def test_golden(name, variant):
         assert_mask_close(mask, g["ref_mask"], what=name)
     else:
         assert mask is None
+
+
+@pytest.mark.parametrize("variant", ["generic", "fast"])
+@pytest.mark.parametrize("name", golden_fullsize_names())
+def test_golden_full_size(name, variant):
+    """The unmodified reference's outputs at the bench feature-map size (120 x 160, 7 views): the fast
+    variants run their compile-time 160 x 120 instantiations here (the dot sweep and the tcgen05 kernel)."""
+    g, inputs, sd = load_golden_fullsize(name)
+    kind = g["kind"]
+    (cost, lowest, planes, mask), used = run_gpu(kind, inputs, g["D"], sd, variant)
+    assert (("fast" in used) or ("tc" in used)) == (variant == "fast"), used
+    assert_cost_close(kind, cost, g["ref_cost"], g["ref_cost64"], what=f"{name}/{variant}", e_ref=g["err32v64"])
+    assert torch.allclose(planes[:, :, 0, 0].cpu(), g["ref_planes"], rtol=3e-7, atol=0)
+    assert_lowest_close(kind, lowest, planes, g["ref_cost"], what=name)
+    if kind == "mlp":
+        assert_mask_close(mask, g["ref_mask"], what=name)
 
 
 # --------------------------------------------------------------------------- #

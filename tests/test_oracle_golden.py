@@ -4,8 +4,8 @@ import pytest
 import torch
 
 from oracle import costvolume_oracle as O
-from tests.parity import (assert_cost_close, assert_lowest_close, assert_mask_close, golden_names,
-                          load_golden)
+from tests.parity import (assert_cost_close, assert_lowest_close, assert_mask_close, golden_fullsize_names,
+                          golden_names, load_golden, load_golden_fullsize)
 
 
 def run_oracle(g, inputs, sd, sampler, dtype=torch.float32):
@@ -33,6 +33,18 @@ def test_oracle_matches_golden(name, sampler):
         assert_mask_close(mask, g["ref_mask"], what=name)
     else:
         assert mask is None
+
+
+@pytest.mark.parametrize("name", golden_fullsize_names())
+def test_oracle_matches_golden_at_the_bench_map_size(name):
+    """120 x 160 x 7 views (tests/golden/make_golden_fullsize.py): regenerated inputs hash to the stored
+    value, and the explicit-sampler oracle (the arithmetic the kernels implement) meets the reference."""
+    g, inputs, sd = load_golden_fullsize(name)
+    cost, lowest, planes, mask = run_oracle(g, inputs, sd, "explicit")
+    assert_cost_close(g["kind"], cost, g["ref_cost"], g["ref_cost64"], what=name, e_ref=g["err32v64"])
+    assert_lowest_close(g["kind"], lowest, planes, g["ref_cost"], what=name)
+    if g["kind"] == "mlp":
+        assert_mask_close(mask, g["ref_mask"], what=name)
 
 
 @pytest.mark.parametrize("name", ["hero_mini_24x32_D8_K7", "cfg0_dot_48x64_D16_K2"])
