@@ -180,3 +180,29 @@ def test_install_against_the_real_reference_module():
         S.uninstall()
     for n, c in orig.items():
         assert getattr(ref_cv, n) is c
+
+
+def test_install_swaps_the_real_reference_loss_class():
+    """install(losses=True) on the UNMODIFIED reference's losses module (build container only): MVDepthLoss
+    resolves to the kernel-backed mirror with the reference's constructor / forward / helper signatures;
+    uninstall() restores it."""
+    from oracle.ref_import import load_reference, reference_available
+    if not reference_available():
+        pytest.skip("reference tree not mounted")
+    load_reference()
+    import importlib
+    ref_losses = importlib.import_module("losses")
+    orig = ref_losses.MVDepthLoss
+    try:
+        patched = S.install(losses=True)
+        assert "losses" in patched and ref_losses.MVDepthLoss is S.MVDepthLoss
+        for name in ("__init__", "forward", "get_valid_mask", "get_error_for_pair"):
+            assert list(inspect.signature(getattr(S.MVDepthLoss, name)).parameters) == \
+                list(inspect.signature(getattr(orig, name)).parameters), name
+        loss = ref_losses.MVDepthLoss(192, 256)                     # depth_model.py:144-147
+        assert loss.height == 192 and loss.width == 256
+        with pytest.raises(RuntimeError):                           # CPU tensors: refused, no fallback
+            loss(*[torch.zeros(1)] * 7)
+    finally:
+        S.uninstall()
+    assert ref_losses.MVDepthLoss is orig
