@@ -339,17 +339,26 @@ def run_reference_arm(args, w, per_gpu):
         t_frame = time.perf_counter() - t0
     budget = 150.0
     n_steps = args.steps + max(1, min(args.warmup, 2))
-    frames = int(max(1, min(per_gpu, budget / (t_frame * n_steps))))
+    share = budget / (t_frame * n_steps)            # frames per step the budget allows
+    frames = int(max(1, min(per_gpu, share)))
+    # Many steps (the no-flag default is 100): even one frame per step would take minutes, so a step
+    # is then a plane subset of ONE frame — the port loops over planes like the reference
+    # (modules/cost_volume.py:305, :557), every plane costs the same, the metric stays per frame.
+    planes_timed = w.planes if share >= 1.0 else int(max(4, min(w.planes, w.planes * share)))
+    import dataclasses
+    w_timed = dataclasses.replace(w, planes=planes_timed)
     tup = make_workload_tuple(w, batch=frames)
     with torch.inference_mode():
         for _ in range(max(1, min(args.warmup, 2))):
-            cpu_port_step(w, tup, weights)
+            cpu_port_step(w_timed, tup, weights)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            cpu_port_step(w, tup, weights)
+            cpu_port_step(w_timed, tup, weights)
         dt = time.perf_counter() - t0
-    fps = frames * args.steps / dt
-    sample = (f"{frames} of the {per_gpu} frames of a batch per step (bounded sample; per-frame metric), "
+    fps = frames * (planes_timed / w.planes) * args.steps / dt
+    what = (f"{frames} of the {per_gpu} frames of a batch per step" if planes_timed == w.planes else
+            f"{planes_timed} of the {w.planes} planes of one frame per step (the port's plane loop is uniform)")
+    sample = (f"{what} (bounded sample; per-frame metric), "
               f"{args.steps} steps, {cores} of {os.cpu_count()} host threads (fastest of a probe; "
               "more threads are slower for these tensor sizes)")
     cfg, _ = workload_config(w, per_gpu, world)
@@ -359,7 +368,7 @@ def run_reference_arm(args, w, per_gpu):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "frames_per_step_timed": frames},
+                         "frames_per_step_timed": frames * planes_timed / w.planes},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)

@@ -7,31 +7,35 @@
 // One persistent CTA per SM walks over row tiles; a tile = 128 rows = a 16 x 2 patch of
 // pixels at four consecutive depth planes.  Warp roles (640 threads):
 //   * 12 BUILDER warps, three threads per row: project, gather (chunk-planar copies of the
-//     features, csrc/srcv_prep.cu) and build the row's 202 metadata channels in registers, split
-//     every value into an fp16 (hi, lo) pair and write them straight into TENSOR MEMORY as the
-//     A operand (tcgen05.st) — the (B,F,H,W) / (B*D,H,W,F) tensors the reference materialises
-//     exist only as 208 TMEM columns per row;
-//   * 1 MMA-issuing thread: layer 1 = 13 x 3 tcgen05.mma (A from TMEM, weights from shared
-//     memory, fp32 accumulator in TMEM):  A_hi W_hi + A_hi W_lo + A_lo W_hi — the bias rides in
-//     the MMA (a constant-one K position against a 16 b1 weight row); layer 2 = 8 x 3
-//     tcgen05.mma into a SECOND accumulator region;
-//   * 4 EPILOGUE warps, one thread per row: after layer 1 they read the accumulator 32 columns
-//     at a time, apply LeakyReLU, split to fp16 (hi, lo) and write the layer-2 A operand back IN
-//     PLACE (a chunk's 32 fp32 columns become its 16 hi + 16 lo operand columns, so nothing else
-//     is touched); after layer 2 they apply bias + LeakyReLU and the 128 -> 1 layer as one dot
-//     product per row and store the cost.
-// Stages are chained by mbarriers (tcgen05.commit for MMA completion).  The roles overlap: the
-// builders gather tile t+1 (L1-bound) while the epilogue warps post-process tile t (ALU-bound)
-// and the tensor pipe runs its MMAs; because layer 2 accumulates into its own TMEM columns, the
-// layer-1 MMAs of tile t+1 start while the layer-2 epilogue of tile t is still running.  The
-// tensor pipe only idles during the layer-1 epilogue.
-// Weights (both layers, hi and lo, 168 KB) stay resident in shared memory for the
-// CTA's lifetime, laid out as K-major no-swizzle core matrices by the pack kernel.
+//     features, csrc/srcv_prep.cu), blend on packed fp32 pairs (FFMA2) and build the row's metadata
+//     channels in registers, split every value into an fp16 (hi, lo) pair and write them straight
+//     into TENSOR MEMORY as the A operand (tcgen05.st) — the (B,F,H,W) / (B*D,H,W,F) tensors the
+//     reference materialises exist only as 192 TMEM columns per row.  Two whole views per thread,
+//     then half of view 2 (slots 0, 1) or the tail (slot 2);
+//   * 1 MMA-issuing thread (elect.sync): layer 1 = 12 x 3 tcgen05.mma (A from TMEM, weights from
+//     shared memory, fp32 accumulator in TMEM):  A_hi W_hi + A_hi W_lo + A_lo W_hi, issued as two
+//     64-column halves; the WHOLE layer-1 bias rides in the MMA — a constant-one K position against
+//     a weight row holding 16 (b1 + the frame's pose-measure contribution), which this warp rewrites
+//     in shared memory when its tiles move on to another frame; layer 2 = 8 x 3 tcgen05.mma in two
+//     K halves, accumulating into the first 128 columns of the tile's own (by then dead) A1 buffer;
+//   * 4 EPILOGUE warps, one thread per row: after each layer-1 half they read the accumulator,
+//     apply LeakyReLU, split to fp16 (hi, lo) and write the layer-2 A operand back IN PLACE (a
+//     chunk's 32 fp32 columns become its 16 hi + 16 lo operand columns, so nothing else is
+//     touched); after layer 2 they apply bias + LeakyReLU and the 128 -> 1 layer as one dot
+//     product per row (packed FFMA2 chains) and store the cost.
+// Stages are chained by mbarriers (tcgen05.commit for MMA completion).  The roles overlap: with two
+// A1 buffers the builders gather tile t+1 while the epilogue warps post-process tile t and the
+// tensor pipe runs its MMAs; the layer-1 MMAs of tile t+1 start while the layer-2 epilogue of tile
+// t is still running; within a tile the epilogue of one half overlaps the MMAs of the other.
+// Weights (both layers, hi and lo, 164 KB) stay resident in shared memory for the CTA's lifetime,
+// laid out as K-major no-swizzle core matrices by the pack kernel.
 //
-// The K order of layer 1 is OURS (the pack kernel permutes W1's columns to match):
-//   per view k (26 channels): 16 warped | mask | z' | dot | ray angle | n_src (3) | comb | r | t
-//   tail (21 + 5 pad):        16 reference features | plane depth | n_cur (3) | ONE (bias) | zeros
-// i.e. a builder thread writes the 3 x 26 (or 2 x 26) consecutive K positions of its blocks.
+// The K order of layer 1 is OURS (the pack kernel permutes W1's columns to match), 8 blocks x 24:
+//   per view k:  16 warped | mask | z' | dot | ray angle | n_src (3) | pad
+//     (view 2, built by two threads:  8 warped | dot | mask | z' | angle || 8 warped | dot | n_src (3))
+//   tail:        16 reference features | plane depth | n_cur (3) | ONE (bias) | pad
+// The 21 pose measures (comb, r, t per view) are constant per (frame, view) and enter through the
+// bias row instead of 21 K positions.
 //
 // Scaling: W1 and W2 are stored x16 (exact) so the lo halves of typical |w| ~ 0.05 weights
 // stay out of the fp16 subnormals.  Layer 1 therefore yields 16 (W1 x + b1); LeakyReLU
