@@ -246,7 +246,6 @@ __device__ __forceinline__ void store_block(uint32_t a1_lane, uint32_t col, cons
 struct RowCtx {
   float dval, dxc, dyc;      // plane depth, centred pixel
   float X, Y, Z;             // back-projected point
-  float cxn, cyn, czn;       // n_cur / max(|n_cur|, eps_cos)  (cosine_similarity operand)
   float cx, cy, cz;          // n_cur
   float4 cur4[4];            // reference-frame features of the pixel
   int b;                     // frame
@@ -345,8 +344,9 @@ __device__ __forceinline__ unsigned view_block(const RowCtx& rc, const ViewParam
   const float sx0 = rc.X - vr.centre[0], sy0 = rc.Y - vr.centre[1], sz0 = rc.Z - vr.centre[2];
   const float is = inv_norm(fmaf(sx0, sx0, fmaf(sy0, sy0, sz0 * sz0)), kEpsNorm);
   const float sx = sx0 * is, sy = sy0 * is, sz = sz0 * is;
-  const float i2 = inv_norm(fmaf(sx, sx, fmaf(sy, sy, sz * sz)), kEpsCos);
-  const float ang = fmaf(rc.cxn, sx * i2, fmaf(rc.cyn, sy * i2, rc.czn * (sz * i2)));
+  // cosine_similarity divides each operand by max(|.|, 1e-5) again (:683-688): both are unit vectors to
+  // an ulp here (or exactly zero, which stays zero), so the plain dot product is the same to ~1e-7
+  const float ang = fmaf(rc.cx, sx, fmaf(rc.cy, sy, rc.cz * sz));
 #pragma unroll
   for (int i = 0; i < 8; ++i) split_pack(v2[i].x, v2[i].y, hi[i], lo[i]);
   split_pack(mk, zp, hi[8], lo[8]);
@@ -443,8 +443,9 @@ __device__ __forceinline__ unsigned unit_issue(const RowCtx& rc, int k, int half
   const float sx0 = rc.X - vr.centre[0], sy0 = rc.Y - vr.centre[1], sz0 = rc.Z - vr.centre[2];
   const float is = inv_norm(fmaf(sx0, sx0, fmaf(sy0, sy0, sz0 * sz0)), kEpsNorm);
   const float sx = sx0 * is, sy = sy0 * is, sz = sz0 * is;
-  const float i2 = inv_norm(fmaf(sx, sx, fmaf(sy, sy, sz * sz)), kEpsCos);
-  const float ang = fmaf(rc.cxn, sx * i2, fmaf(rc.cyn, sy * i2, rc.czn * (sz * i2)));
+  // cosine_similarity divides each operand by max(|.|, 1e-5) again (:683-688): both are unit vectors to
+  // an ulp here (or exactly zero, which stays zero), so the plain dot product is the same to ~1e-7
+  const float ang = fmaf(rc.cx, sx, fmaf(rc.cy, sy, rc.cz * sz));
   uc.mk = mk;
   uc.e0 = half ? sx : mk;
   uc.e1 = half ? sy : zp;
@@ -532,14 +533,23 @@ __device__ __forceinline__ void issue_steps(uint32_t d, uint32_t a_base, uint32_
 
 // tile id runs plane-chunk fastest, then pixel patch, then frame (32-bit: the launcher
 // refuses >= 2^31 tiles); row -> (plane-in-chunk = row / 32, pixel of the 16 x 2 patch = row % 32)
+// id / nd for the runtime plane-chunk count nd: multiply-high by ceil(2^32 / nd), exact while
+// id * nd < 2^32 (the launcher refuses larger volumes) — 2 instructions instead of the ~20 of a
+// generic 32-bit division, in every warp of every tile.
+struct DivNd {
+  unsigned nd, magic;
+  __device__ __forceinline__ explicit DivNd(unsigned n) : nd(n), magic((unsigned)((0x100000000ull + n - 1) / n)) {}
+  __device__ __forceinline__ unsigned div(unsigned id) const { return nd == 1u ? id : __umulhi(id, magic); }
+};
+
 template <bool PER_PIXEL>
-__device__ __forceinline__ void make_row(unsigned id, int row, int W, int H, int HW, int D, unsigned nd,
+__device__ __forceinline__ void make_row(unsigned id, int row, int W, int H, int HW, int D, const DivNd& nd,
                                          unsigned tiles_x, unsigned tiles_xy, const Centre& ctr,
                                          const float4* __restrict__ cur4g,
                                          const FrameParams* __restrict__ frames,
                                          const float* __restrict__ planes, RowCtx& rc) {
-  const int d0 = (int)(id % nd) * kTileD;
-  const unsigned r = id / nd;
+  const unsigned r = nd.div(id);
+  const int d0 = (int)(id - r * nd.nd) * kTileD;
   const unsigned txy = r % tiles_xy;
   const int b = (int)(r / tiles_xy);
   const int x0 = (int)(txy % tiles_x) * kTileW, y0 = (int)(txy / tiles_x) * kTileH;
@@ -567,8 +577,6 @@ __device__ __forceinline__ void make_row(unsigned id, int row, int W, int H, int
   rc.X = rc.dval * rxv; rc.Y = rc.dval * ryv; rc.Z = rc.dval * rzv;
   const float ic = inv_norm(fmaf(rc.X, rc.X, fmaf(rc.Y, rc.Y, rc.Z * rc.Z)), kEpsNorm);
   rc.cx = rc.X * ic; rc.cy = rc.Y * ic; rc.cz = rc.Z * ic;
-  const float i1 = inv_norm(fmaf(rc.cx, rc.cx, fmaf(rc.cy, rc.cy, rc.cz * rc.cz)), kEpsCos);
-  rc.cxn = rc.cx * i1; rc.cyn = rc.cy * i1; rc.czn = rc.cz * i1;
 }
 
 // K block `blk` (0..6: source view, 7: view-independent tail) of a row -> packed (hi, lo)
@@ -615,7 +623,7 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
   constexpr int HWC = TW * TH;
   const unsigned tiles_x = (unsigned)(W + kTileW - 1) / kTileW;
   const unsigned tiles_xy = tiles_x * ((unsigned)(H + kTileH - 1) / kTileH);
-  const unsigned nd = (unsigned)(D + kTileD - 1) / kTileD;
+  const DivNd nd((unsigned)(D + kTileD - 1) / kTileD);
 
   // ---- one-time setup ----------------------------------------------------------------
   if (tid == 0) {
@@ -730,8 +738,8 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
       int b;
       {
         const unsigned id = tile_id(it);
-        const int d0 = (int)(id % nd) * kTileD;
-        const unsigned r = id / nd, txy = r % tiles_xy;
+        const unsigned r = nd.div(id), txy = r % tiles_xy;
+        const int d0 = (int)(id - r * nd.nd) * kTileD;
         b = (int)(r / tiles_xy);
         const int x0 = (int)(txy % tiles_x) * kTileW, y0 = (int)(txy / tiles_x) * kTileH;
         const int rx = row & (kTileW - 1), ry = (row >> 4) & (kTileH - 1), dd = row >> 5;
@@ -835,7 +843,7 @@ mlp_tc_kernel(srcv_shape s, const float4* __restrict__ cur4g, const float4* __re
         // K position: rewritten (fp16 hi, lo) when the CTA's tiles move on to another frame.  Its
         // readers — the layer-1 MMAs of earlier tiles — completed before this warp issued the
         // previous tile's last layer-2 MMAs (bar_mma1 -> epilogue -> bar_a2_full -> here).
-        const int fb = (int)(tile_id(it) / (nd * tiles_xy));
+        const int fb = (int)(nd.div(tile_id(it)) / tiles_xy);
         if (fb != bias_frame) {
           bias_frame = fb;
 #pragma unroll
@@ -1026,7 +1034,8 @@ cudaError_t launch_mlp_tc(const srcv_shape& s, const float* cur, const Workspace
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles_x = (s.W + kTileW - 1) / kTileW, tiles_y = (s.H + kTileH - 1) / kTileH;
   const long long num_tiles = (long long)s.B * ((s.D + kTileD - 1) / kTileD) * tiles_x * tiles_y;
-  if (num_tiles >= (1ll << 31)) return cudaErrorInvalidValue;   // tile ids are 32-bit
+  // tile ids are 32-bit, and the kernel's multiply-high division by the plane-chunk count is exact below 2^32 / nd
+  if (num_tiles >= (1ll << 31) || num_tiles * ((s.D + kTileD - 1) / kTileD) >= (1ll << 32)) return cudaErrorInvalidValue;
   const int grid = (int)(num_tiles < sms ? num_tiles : sms);
   const float4* src4 = reinterpret_cast<const float4*>(ws.src_c4);
   const float4* cur4 = reinterpret_cast<const float4*>(ws.cur_c4);

@@ -142,6 +142,7 @@ inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst
 template <class T> inline T __ldg(const T* p) { return *p; }
 template <class T> inline T __ldcg(const T* p) { return *p; }
 
+inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 inline float __fadd_rn(float a, float b) { return a + b; }   // built with -ffp-contract=off
 inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fdiv_rn(float a, float b) { return a / b; }
