@@ -337,7 +337,7 @@ def run_reference_arm(args, w, per_gpu):
         t0 = time.perf_counter()
         cpu_port_step(w, one, weights)
         t_frame = time.perf_counter() - t0
-    budget = 150.0
+    budget = float(os.environ.get("SRCV_REF_BUDGET_S", "150"))   # seconds for the whole run (tests shrink it)
     n_steps = args.steps + max(1, min(args.warmup, 2))
     share = budget / (t_frame * n_steps)            # frames per step the budget allows
     frames = int(max(1, min(per_gpu, share)))

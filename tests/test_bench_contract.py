@@ -22,6 +22,20 @@ def test_reference_arm_prints_contract_line():
     assert line["config"]["workload"].startswith("cfg0")
 
 
+def test_reference_arm_stays_bounded_at_many_steps():
+    """At large step counts (the no-flag default is 100) a step becomes a plane subset of one frame, the
+    metric stays per frame and the run stays within its budget."""
+    import os
+    env = dict(os.environ, SRCV_REF_BUDGET_S="0.02", SRCV_CPU_THREADS="2")
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--workload", "cfg0",
+                        "--steps", "12", "--warmup", "3"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    cb = line["cpu_baseline"]
+    assert "planes of one frame per step" in cb["sample"] and 0 < cb["frames_per_step_timed"] < 1
+    assert line["steps"] == 12 and line["value"] > 0 and line["config"]["workload"].startswith("cfg0")
+
+
 def test_algorithmic_bytes_match_survey():
     sys.path.insert(0, str(ROOT))
     import bench
