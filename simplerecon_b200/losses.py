@@ -57,7 +57,10 @@ class _Call:
                              ("src_cam_T_world_bk44", src_cam_T_world, (B, K, 4, 4))):
             if tuple(m.shape) != shp:
                 raise ValueError(f"{name} must be {shp}, got {tuple(m.shape)}")
-        self.t = [_f32c(x) for x in (depth_pred, cur_depth, src_depth, cur_invK, src_K, cur_world_T_cam, src_cam_T_world)]
+        tensors = (depth_pred, cur_depth, src_depth, cur_invK, src_K, cur_world_T_cam, src_cam_T_world)
+        if any(x.device != depth_pred.device for x in tensors):
+            raise ValueError("MVDepthLoss inputs live on different devices: " + ", ".join(str(x.device) for x in tensors))
+        self.t = [_f32c(x) for x in tensors]
         self.B, self.K, self.H, self.W = B, K, H, W
         self.args = _native.MvLossArgs(*[C.c_void_p(x.data_ptr()) for x in self.t], B, K, H, W)
         self.device = self.t[0].device
